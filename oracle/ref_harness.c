@@ -1,0 +1,115 @@
+/* ref_harness.c -- TEST INFRASTRUCTURE ONLY (checker / CPU baseline), never linked into the product.
+ *
+ * A thin caller of the UNMODIFIED reference GRIMM 2.01 functions, compiled together with the
+ * reference's own object files (everything except mcmain.o) into oracle/_ref/libgrimmref.so by
+ * oracle/Makefile.  No reference arithmetic is restated here: every number returned comes out of
+ * the reference's invdist_noncircular_v (G/uniinvdist.c:235) or print_scenario_2
+ * (G/opt_scenario.c:73).  The reference parser's MAX_NUM_GENES limit (G/mcstructs.h:42) is
+ * not involved because genomes arrive as arrays.
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include "mcstructs.h"
+#include "uniinvdist.h"
+#include "mcrdist.h"
+#include "scenario.h"
+#include "opt_scenario.h"
+
+FILE *outfile; /* the global the reference prints to (defined in G/mcmain.c:66, which we leave out) */
+
+static void stats_one(const int *gamma, const int *pi, int n, distmem_t *dm, int *out5)
+{
+  struct genome_struct g1, g2;
+  graphstats_t gs;
+  memset(&g1, 0, sizeof g1);
+  memset(&g2, 0, sizeof g2);
+  g1.genes = (int *)gamma;
+  g2.genes = (int *)pi;
+  invdist_noncircular_v(&g1, &g2, 0, n, dm, &gs);
+  out5[0] = gs.d; out5[1] = gs.br; out5[2] = gs.c4; out5[3] = gs.h; out5[4] = gs.f;
+}
+
+/* one pair: out5 = {d, b, c, h, f} */
+int ref_dist_stats(const int *gamma, const int *pi, int n, int *out5)
+{
+  distmem_t dm;
+  mcdist_allocmem(n, 0, &dm);
+  stats_one(gamma, pi, n, &dm, out5);
+  mcdist_freemem(&dm);
+  return out5[0];
+}
+
+typedef struct {
+  const int *genomes; int n;
+  const int *pairs; long lo, hi;
+  int *out; int stride;
+} job_t;
+
+static void *worker(void *arg)
+{
+  job_t *j = (job_t *)arg;
+  distmem_t dm;
+  int tmp[5];
+  long p;
+  mcdist_allocmem(j->n, 0, &dm);
+  for (p = j->lo; p < j->hi; p++) {
+    const int *ga = j->genomes + (long)j->pairs[2*p] * j->n;
+    const int *pi = j->genomes + (long)j->pairs[2*p+1] * j->n;
+    stats_one(ga, pi, j->n, &dm, tmp);
+    if (j->stride == 1) j->out[p] = tmp[0];
+    else memcpy(j->out + 5*p, tmp, sizeof tmp);
+  }
+  mcdist_freemem(&dm);
+  return NULL;
+}
+
+/* pairs[2p] = gamma index, pairs[2p+1] = pi index (setinvmatrix order, G/uniinvdist.c:80-90).
+ * stride 1 -> out[p] = d ; stride 5 -> out[5p..] = {d,b,c,h,f}.  nthreads host threads, each with
+ * its own distmem_t exactly like one reference process would have. */
+void ref_dist_pairs(const int *genomes, int n, const int *pairs, long npairs,
+                    int *out, int stride, int nthreads)
+{
+  int t;
+  if (nthreads < 1) nthreads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  job_t *jobs = (job_t *)malloc(sizeof(job_t) * nthreads);
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].genomes = genomes; jobs[t].n = n; jobs[t].pairs = pairs;
+    jobs[t].lo = npairs * t / nthreads; jobs[t].hi = npairs * (t + 1) / nthreads;
+    jobs[t].out = out; jobs[t].stride = stride;
+    pthread_create(&th[t], NULL, worker, &jobs[t]);
+  }
+  for (t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+/* Run the reference's default -s engine (scenario_type 4, G/mcmain.c:240,948) from src to dst and
+ * return the step list parsed back out of the text it prints: steps[2k]=start, steps[2k+1]=end.
+ * Returns the number of steps, or -1 if more than maxsteps.  Not thread-safe (global outfile). */
+int ref_scenario(const int *src, const int *dst, int n, int *steps, int maxsteps)
+{
+  struct genome_struct g1, g2;
+  char *buf = NULL; size_t len = 0;
+  FILE *saved = outfile;
+  int nsteps = 0;
+  char *p;
+  memset(&g1, 0, sizeof g1); memset(&g2, 0, sizeof g2);
+  g1.genes = (int *)src; g2.genes = (int *)dst;
+  outfile = open_memstream(&buf, &len);
+  print_scenario_2(&g1, &g2, n, 0, 4);
+  fclose(outfile);
+  outfile = saved;
+  for (p = buf; (p = strstr(p, "Step ")) != NULL; p += 5) {
+    int k, s, sv, e, ev;
+    if (sscanf(p, "Step %d: Chrom. 0, gene %d [%d] through chrom. 0, gene %d [%d]",
+               &k, &s, &sv, &e, &ev) == 5) {
+      if (nsteps >= maxsteps) { free(buf); return -1; }
+      steps[2*nsteps] = s; steps[2*nsteps+1] = e; nsteps++;
+    }
+  }
+  free(buf);
+  return nsteps;
+}
