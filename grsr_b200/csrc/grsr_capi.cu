@@ -1,0 +1,450 @@
+// grsr_capi.cu -- the C ABI declared in include/grsr.h: argument checks, device buffers, copies,
+// launches and the multi-GPU pair-list sharder.  All arithmetic of the path happens in the kernels
+// of grsr_core.cuh / grsr_scenario.cuh; there is no host implementation of it here.
+#include "../../include/grsr.h"
+#include "grsr_core.cuh"
+#include "grsr_scenario.cuh"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(GRSR_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));        \
+  } while (0)
+
+struct DevInfo { int sms = 0; int smem_optin = 0; bool ok = false; };
+
+int dev_info(int dev, DevInfo &di) {
+  static std::mutex mu;
+  static std::vector<DevInfo> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= dev) cache.resize(dev + 1);
+  if (!cache[dev].ok) {
+    CK(cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&cache[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cache[dev].ok = true;
+  }
+  di = cache[dev];
+  return GRSR_OK;
+}
+
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+// threads per block for the one-pair-per-block kernels: enough lanes to cover the 2n+2 vertices a
+// few times per pass, small enough that several blocks stay resident per SM.
+int pick_threads(int n) {
+  int t = env_int("GRSR_THREADS", 0);
+  if (t >= 32 && t <= 256 && (t % 32) == 0) return t;
+  int size = 2 * n + 2;
+  if (size <= 128) return 32;
+  if (size <= 512) return 64;
+  if (size <= 2048) return 128;
+  return 256;
+}
+
+struct Launch { int threads; int grid; size_t smem; };
+
+template <class K>
+int plan_launch(K kernel, int n, bool keep_orbits, long long units, Launch &L) {
+  int dev;
+  CK(cudaGetDevice(&dev));
+  DevInfo di;
+  int rc = dev_info(dev, di);
+  if (rc) return rc;
+  L.smem = grsr::work_bytes(n, keep_orbits);
+  if (n > grsr::kMaxSmemGenes || L.smem > (size_t)di.smem_optin || 2 * n + 2 > 65535)
+    return fail(GRSR_ERR_TOOLARGE,
+                "num_genes=%d needs %zu bytes of shared memory per pair; this build keeps the "
+                "breakpoint graph on chip and accepts at most %d genes",
+                n, L.smem, grsr_max_genes());
+  L.threads = pick_threads(n);
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, L.threads, L.smem));
+  if (occ < 1) return fail(GRSR_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", L.smem);
+  occ = env_int("GRSR_OCC", occ) < occ ? env_int("GRSR_OCC", occ) : occ;
+  long long g = (long long)di.sms * occ;   // a whole number of resident waves: 148 SMs x occupancy
+  if (g > units) g = units;
+  if (g < 1) g = 1;
+  L.grid = (int)g;
+  return GRSR_OK;
+}
+
+__global__ void triangle_pairs_kernel(int G, long long first, long long count, int32_t *pairs) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
+    long long p = first + q;
+    double t = 2.0 * G - 1.0;
+    long long i = (long long)((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
+    if (i < 0) i = 0;
+    while (i > 0 && i * (2LL * G - i - 1) / 2 > p) i--;
+    while ((i + 1) * (2LL * G - (i + 1) - 1) / 2 <= p) i++;
+    long long j = i + 1 + (p - i * (2LL * G - i - 1) / 2);
+    pairs[2 * q] = (int32_t)i; pairs[2 * q + 1] = (int32_t)j;
+  }
+}
+
+__global__ void square_pairs_kernel(int G, long long first, long long count, int32_t *pairs) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
+    long long p = first + q;
+    pairs[2 * q] = (int32_t)(p / G); pairs[2 * q + 1] = (int32_t)(p % G);
+  }
+}
+
+int check_device_range(int first_device, int ngpus) {
+  int cnt = grsr_device_count();
+  if (cnt <= 0)
+    return fail(GRSR_ERR_NODEVICE, "no CUDA device is available; libgrsr_cuda has no CPU path");
+  if (ngpus < 1 || first_device < 0 || first_device + ngpus > cnt)
+    return fail(GRSR_ERR_NODEVICE, "devices %d..%d requested but %d CUDA device(s) present",
+                first_device, first_device + ngpus - 1, cnt);
+  return GRSR_OK;
+}
+
+// check_genes of the reference (G/mcread_input.c:83-135): every row a signed permutation of 1..n
+int check_genomes(const int32_t *genomes, long long rows, int n) {
+  if (!genomes || n < 1 || rows < 1) return fail(GRSR_ERR_INVALID, "empty genome table");
+  std::vector<unsigned char> seen((size_t)n + 1);
+  for (long long r = 0; r < rows; r++) {
+    memset(seen.data(), 0, seen.size());
+    const int32_t *g = genomes + r * n;
+    for (int i = 0; i < n; i++) {
+      long long a = g[i] < 0 ? -(long long)g[i] : g[i];
+      if (a == 0) return fail(GRSR_ERR_INVALID, "genome %lld: input gene == 0", r + 1);
+      if (a > n)
+        return fail(GRSR_ERR_INVALID, "genome %lld: input gene (%d) larger than number of genes %d",
+                    r + 1, g[i], n);
+      if (seen[a]) return fail(GRSR_ERR_INVALID, "genome %lld: duplicate gene (%lld)", r + 1, a);
+      seen[a] = 1;
+    }
+  }
+  return GRSR_OK;
+}
+
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    if (p) { cudaFree(p); p = nullptr; }
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return GRSR_OK;
+  }
+};
+
+enum PairSource { PAIRS_LIST, PAIRS_TRIANGLE, PAIRS_SQUARE };
+
+// One device's share of a pair job: copy the genome table in, build the signed inverses, obtain the
+// pair slice (copied or generated on the device), run the kernel, copy the results out.
+int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSource src,
+                        const int32_t *pairs_host, long long first, long long count,
+                        int32_t *out_host, int stride) {
+  if (count <= 0) return GRSR_OK;
+  CK(cudaSetDevice(dev));
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DevBuf dg, ds, dp, dout;
+  size_t gbytes = (size_t)G * n * sizeof(int32_t);
+  int rc;
+  if ((rc = dg.alloc(gbytes)) || (rc = ds.alloc(gbytes)) ||
+      (rc = dp.alloc((size_t)count * 2 * sizeof(int32_t))) ||
+      (rc = dout.alloc((size_t)count * stride * sizeof(int32_t)))) {
+    cudaStreamDestroy(st);
+    return rc;
+  }
+  auto body = [&]() -> int {
+    CK(cudaMemcpyAsync(dg.p, genomes, gbytes, cudaMemcpyHostToDevice, st));
+    int r = grsr_signed_inverse_dev((const int32_t *)dg.p, G, n, (int32_t *)ds.p, st);
+    if (r) return r;
+    if (src == PAIRS_LIST) {
+      CK(cudaMemcpyAsync(dp.p, pairs_host + 2 * first, (size_t)count * 2 * sizeof(int32_t),
+                         cudaMemcpyHostToDevice, st));
+    } else if (src == PAIRS_TRIANGLE) {
+      r = grsr_triangle_pairs_dev(G, first, count, (int32_t *)dp.p, st);
+      if (r) return r;
+    } else {
+      int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+      square_pairs_kernel<<<blocks, 256, 0, st>>>(G, first, count, (int32_t *)dp.p);
+      CK(cudaGetLastError());
+    }
+    r = grsr_dist_pairs_dev((const int32_t *)dg.p, (const int32_t *)ds.p, n, (const int32_t *)dp.p,
+                            count, (int32_t *)dout.p, stride, st);
+    if (r) return r;
+    CK(cudaMemcpyAsync(out_host, dout.p, (size_t)count * stride * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GRSR_OK;
+  };
+  rc = body();
+  cudaStreamDestroy(st);
+  return rc;
+}
+
+// Split [0, total) into ngpus contiguous slices, one host thread per device; no data-path collective.
+int shard_pairs(const int32_t *genomes, int G, int n, PairSource src, const int32_t *pairs_host,
+                long long total, int32_t *out_host, int stride, int first_device, int ngpus) {
+  if (ngpus == 1)
+    return run_pairs_on_device(first_device, genomes, G, n, src, pairs_host, 0, total, out_host,
+                               stride);
+  std::vector<int> rcs(ngpus, 0);
+  std::vector<std::string> errs(ngpus);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ngpus; d++) {
+    long long lo = total * d / ngpus, hi = total * (d + 1) / ngpus;
+    th.emplace_back([&, d, lo, hi]() {
+      rcs[d] = run_pairs_on_device(first_device + d, genomes, G, n, src, pairs_host, lo, hi - lo,
+                                   out_host + lo * stride, stride);
+      if (rcs[d]) errs[d] = g_err;
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int d = 0; d < ngpus; d++)
+    if (rcs[d]) return fail(rcs[d], "device %d: %s", first_device + d, errs[d].c_str());
+  return GRSR_OK;
+}
+
+// One device's share of a scenario batch: copy the pairs in, run the persistent scenario kernel,
+// copy the step lists out.
+int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npairs, int n,
+                       grsr_step_t *steps, int32_t *nsteps, int max_steps) {
+  if (npairs <= 0) return GRSR_OK;
+  CK(cudaSetDevice(dev));
+  DevInfo di;
+  int rc = dev_info(dev, di);
+  if (rc) return rc;
+  size_t smem = grsr::work_bytes(n, true) + grsr::scen_extra_bytes(n);
+  if (n > grsr_max_genes() || smem > (size_t)di.smem_optin)
+    return fail(GRSR_ERR_TOOLARGE,
+                "num_genes=%d needs %zu bytes of shared memory per scenario; this build accepts at "
+                "most %d genes", n, smem, grsr_max_genes());
+  int threads = pick_threads(n);
+  CK(cudaFuncSetAttribute(grsr::scenario_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, grsr::scenario_kernel, threads, smem));
+  if (occ < 1) return fail(GRSR_ERR_CUDA, "scenario kernel does not fit on an SM");
+  long long grid = (long long)di.sms * occ;
+  if (grid > npairs) grid = npairs;
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DevBuf dsrc, ddst, dsteps, dns, dstat, dtick;
+  size_t gbytes = (size_t)npairs * n * sizeof(int32_t);
+  size_t sbytes = (size_t)npairs * (max_steps > 0 ? max_steps : 1) * sizeof(grsr_step_t);
+  if ((rc = dsrc.alloc(gbytes)) || (rc = ddst.alloc(gbytes)) || (rc = dsteps.alloc(sbytes)) ||
+      (rc = dns.alloc((size_t)npairs * 4)) || (rc = dstat.alloc((size_t)npairs * 4)) ||
+      (rc = dtick.alloc(4))) {
+    cudaStreamDestroy(st);
+    return rc;
+  }
+  std::vector<int32_t> stat((size_t)npairs);
+  auto body = [&]() -> int {
+    CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dtick.p, 0, 4, st));
+    grsr::scenario_kernel<<<(int)grid, threads, smem, st>>>(
+        (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
+        (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(steps, dsteps.p, sbytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(nsteps, dns.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(stat.data(), dstat.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GRSR_OK;
+  };
+  rc = body();
+  cudaStreamDestroy(st);
+  if (rc) return rc;
+  for (int p = 0; p < npairs; p++) {
+    if (stat[p] == GRSR_SCEN_OVERFLOW)
+      return fail(GRSR_ERR_INVALID, "pair %d: scenario needs more than max_steps=%d steps", p,
+                  max_steps);
+    if (stat[p] == GRSR_SCEN_STUCK)
+      return fail(GRSR_ERR_SEARCH, "pair %d: reversals ended prematurely after %d steps", p,
+                  nsteps[p]);
+  }
+  return GRSR_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int grsr_abi_version(void) { return 1; }
+
+const char *grsr_last_error(void) { return g_err.c_str(); }
+
+int grsr_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
+int grsr_max_genes(void) {
+  int n = grsr::kMaxSmemGenes;
+  while (n > 1 && (grsr::work_bytes(n, true) + grsr::scen_extra_bytes(n) > 227u * 1024u ||
+                   2 * n + 2 > 65535))
+    n--;
+  return n;
+}
+
+int grsr_signed_inverse_dev(const int32_t *d_genomes, int num_genomes, int num_genes,
+                            int32_t *d_sinv, void *stream) {
+  long long total = (long long)num_genomes * num_genes;
+  if (total <= 0) return fail(GRSR_ERR_INVALID, "empty genome table");
+  int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  grsr::signed_inverse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_genomes, d_sinv, total,
+                                                                         num_genes);
+  CK(cudaGetLastError());
+  return GRSR_OK;
+}
+
+int grsr_triangle_pairs_dev(int num_genomes, int64_t first, int64_t count, int32_t *d_pairs,
+                            void *stream) {
+  if (count <= 0) return GRSR_OK;
+  int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+  triangle_pairs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(num_genomes, first, count, d_pairs);
+  CK(cudaGetLastError());
+  return GRSR_OK;
+}
+
+int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
+                        const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
+                        void *stream) {
+  if (npairs <= 0) return GRSR_OK;
+  if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
+  if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
+  Launch L;
+  int rc = plan_launch(grsr::dist_pairs_kernel, num_genes, false, npairs, L);
+  if (rc) return rc;
+  grsr::dist_pairs_kernel<<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
+      d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride);
+  CK(cudaGetLastError());
+  return GRSR_OK;
+}
+
+int grsr_dist_pairs(const int32_t *genomes, int num_genomes, int num_genes, const int32_t *pairs,
+                    int64_t npairs, int32_t *out, int stride, int first_device, int ngpus) {
+  int rc = check_device_range(first_device, ngpus);
+  if (rc) return rc;
+  if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
+  if (npairs < 0 || (npairs > 0 && (!pairs || !out))) return fail(GRSR_ERR_INVALID, "null buffer");
+  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  for (int64_t p = 0; p < 2 * npairs; p++)
+    if (pairs[p] < 0 || pairs[p] >= num_genomes)
+      return fail(GRSR_ERR_INVALID, "pair %lld names genome %d of %d", (long long)(p / 2),
+                  pairs[p], num_genomes);
+  if (npairs == 0) return GRSR_OK;
+  return shard_pairs(genomes, num_genomes, num_genes, PAIRS_LIST, pairs, npairs, out, stride,
+                     first_device, ngpus);
+}
+
+int grsr_dist_matrix_shard(const int32_t *genomes, int num_genomes, int num_genes, int shard,
+                           int num_shards, int32_t *out, int64_t *count, int device) {
+  int rc = check_device_range(device, 1);
+  if (rc) return rc;
+  if (num_shards < 1 || shard < 0 || shard >= num_shards || !out || !count)
+    return fail(GRSR_ERR_INVALID, "bad shard %d of %d", shard, num_shards);
+  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  long long P = (long long)num_genomes * (num_genomes - 1) / 2;
+  long long lo = P * shard / num_shards, hi = P * (shard + 1) / num_shards;
+  *count = hi - lo;
+  return run_pairs_on_device(device, genomes, num_genomes, num_genes, PAIRS_TRIANGLE, nullptr, lo,
+                             hi - lo, out, 1);
+}
+
+int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes, int32_t *distmatrix,
+                     int first_device, int ngpus) {
+  int rc = check_device_range(first_device, ngpus);
+  if (rc) return rc;
+  if (!distmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
+  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  long long G = num_genomes, P = G * (G - 1) / 2;
+  std::vector<int32_t> flat((size_t)(P > 0 ? P : 1));
+  if (P > 0) {
+    rc = shard_pairs(genomes, num_genomes, num_genes, PAIRS_TRIANGLE, nullptr, P, flat.data(), 1,
+                     first_device, ngpus);
+    if (rc) return rc;
+  }
+  // host gather of matrix rows: distmatrix[i][j] = distmatrix[j][i] (G/uniinvdist.c:84-88)
+  long long p = 0;
+  for (long long i = 0; i < G; i++) {
+    distmatrix[i * G + i] = 0;
+    for (long long j = i + 1; j < G; j++, p++)
+      distmatrix[i * G + j] = distmatrix[j * G + i] = flat[p];
+  }
+  return GRSR_OK;
+}
+
+int grsr_stats_matrix(const int32_t *genomes, int num_genomes, int num_genes,
+                      grsr_stats_t *statsmatrix, int first_device, int ngpus) {
+  int rc = check_device_range(first_device, ngpus);
+  if (rc) return rc;
+  if (!statsmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
+  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  long long total = (long long)num_genomes * num_genomes;
+  return shard_pairs(genomes, num_genomes, num_genes, PAIRS_SQUARE, nullptr, total,
+                     (int32_t *)statsmatrix, 5, first_device, ngpus);
+}
+
+int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int num_genes,
+                        grsr_step_t *steps, int32_t *nsteps, int max_steps, int first_device,
+                        int ngpus) {
+  int rc = check_device_range(first_device, ngpus);
+  if (rc) return rc;
+  if (npairs < 0 || max_steps < 0 || (npairs > 0 && (!steps || !nsteps)))
+    return fail(GRSR_ERR_INVALID, "bad scenario arguments");
+  if (npairs == 0) return GRSR_OK;
+  if ((rc = check_genomes(src, npairs, num_genes))) return rc;
+  if ((rc = check_genomes(dst, npairs, num_genes))) return rc;
+  std::vector<int> rcs(ngpus, 0);
+  std::vector<std::string> errs(ngpus);
+  auto work = [&](int d) {
+    long long lo = (long long)npairs * d / ngpus, hi = (long long)npairs * (d + 1) / ngpus;
+    rcs[d] = scenario_on_device(first_device + d, src + lo * num_genes, dst + lo * num_genes,
+                                      (int)(hi - lo), num_genes, steps + lo * max_steps,
+                                      nsteps + lo, max_steps);
+    if (rcs[d]) errs[d] = g_err;
+  };
+  if (ngpus == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (int d = 0; d < ngpus; d++) th.emplace_back(work, d);
+    for (auto &t : th) t.join();
+  }
+  for (int d = 0; d < ngpus; d++)
+    if (rcs[d]) return fail(rcs[d], "device %d: %s", first_device + d, errs[d].c_str());
+  return GRSR_OK;
+}
+
+} // extern "C"
