@@ -1,0 +1,200 @@
+"""Test helpers: ctypes bindings of the oracle (oracle/liboracle.so), of the reference harness
+(oracle/_ref/libgrimmref.so, when it has been built) and of the emulated kernels."""
+from __future__ import annotations
+
+import ctypes
+import itertools
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I32P = ctypes.POINTER(ctypes.c_int)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "grimm")
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")
+EXAMPLE = os.path.join(GOLDEN, "example_mgr_macro.txt")
+
+
+def _p(a):
+    return a.ctypes.data_as(I32P)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+_orc = None
+
+
+def oracle():
+    global _orc
+    if _orc is None:
+        _orc = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    return _orc
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_LIB) and os.path.exists(REF_BIN)
+
+
+_ref = None
+
+
+def reference():
+    global _ref
+    if _ref is None:
+        _ref = ctypes.CDLL(REF_LIB)
+    return _ref
+
+
+def orc_stats(genomes, pairs) -> np.ndarray:
+    g = _i32(genomes)
+    pr = _i32(pairs).reshape(-1, 2)
+    out = np.zeros((len(pr), 5), dtype=np.int32)
+    oracle().orc_dist_pairs(_p(g), g.shape[1], _p(pr), ctypes.c_long(len(pr)), _p(out), 5)
+    return out
+
+
+def ref_stats(genomes, pairs, threads: int = 4) -> np.ndarray:
+    g = _i32(genomes)
+    pr = _i32(pairs).reshape(-1, 2)
+    out = np.zeros((len(pr), 5), dtype=np.int32)
+    reference().ref_dist_pairs(_p(g), g.shape[1], _p(pr), ctypes.c_long(len(pr)), _p(out), 5, threads)
+    return out
+
+
+def orc_scenario(src, dst):
+    s = _i32(src)
+    d = _i32(dst)
+    n = len(s)
+    steps = np.zeros(2 * (n + 2), dtype=np.int32)
+    ev = np.zeros(n + 2, dtype=np.int64)
+    k = oracle().orc_scenario(_p(s), _p(d), n, _p(steps), n + 2,
+                              ev.ctypes.data_as(ctypes.POINTER(ctypes.c_long)))
+    assert k >= 0, k
+    return steps[:2 * k].reshape(-1, 2).copy(), int(ev[:k].sum())
+
+
+def ref_scenario(src, dst):
+    s = _i32(src)
+    d = _i32(dst)
+    n = len(s)
+    steps = np.zeros(2 * (n + 2), dtype=np.int32)
+    k = reference().ref_scenario(_p(s), _p(d), n, _p(steps), n + 2)
+    assert k >= 0, k
+    return steps[:2 * k].reshape(-1, 2).copy()
+
+
+def orc_circular_align(genomes) -> np.ndarray:
+    g = _i32(genomes).copy()
+    oracle().orc_circular_align(_p(g), g.shape[0], g.shape[1])
+    return g
+
+
+def apply_steps(src, steps) -> np.ndarray:
+    cur = np.array(src, dtype=np.int64)
+    for s, e in steps:
+        cur[s:e + 1] = -cur[s:e + 1][::-1]
+    return cur
+
+
+def all_signed_perms(n: int) -> np.ndarray:
+    rows = []
+    for p in itertools.permutations(range(1, n + 1)):
+        for s in range(1 << n):
+            rows.append([(-x if (s >> k) & 1 else x) for k, x in enumerate(p)])
+    return np.asarray(rows, dtype=np.int32)
+
+
+_emu = None
+
+
+def emulator():
+    global _emu
+    if _emu is None:
+        from grsr_b200 import build
+        build.build_emu()
+        _emu = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libgrsr_emu.so"))
+    return _emu
+
+
+def emu_stats(genomes, pairs, threads: int = 64, grid: int = 2) -> np.ndarray:
+    g = _i32(genomes)
+    pr = _i32(pairs).reshape(-1, 2)
+    out = np.zeros((len(pr), 5), dtype=np.int32)
+    emulator().emu_dist_pairs(_p(g), g.shape[0], g.shape[1], _p(pr), ctypes.c_longlong(len(pr)), _p(out),
+                              5, threads, grid)
+    return out
+
+
+def emu_scenario(srcs, dsts, threads: int = 64, grid: int = 2):
+    S = _i32(srcs)
+    D = _i32(dsts)
+    npairs, n = S.shape
+    ms = n + 1
+    steps = np.zeros((npairs, ms, 2), dtype=np.int32)
+    ns = np.zeros(npairs, dtype=np.int32)
+    st = np.zeros(npairs, dtype=np.int32)
+    ev = np.zeros(npairs, dtype=np.uint64)
+    emulator().emu_scenario(_p(S), _p(D), npairs, n, _p(steps), _p(ns), ms, _p(st),
+                            ev.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), threads, grid)
+    return [steps[p, :ns[p]].copy() for p in range(npairs)], st, ev
+
+
+def mixed_genomes(n: int, count: int, seed: int) -> np.ndarray:
+    """identity + a seeded mix of random, few-reversal and hurdle/fortress-rich genomes."""
+    import random
+
+    from grsr_b200 import gen
+    rows = [list(range(1, n + 1))]
+    for s in range(count - 1):
+        rng = random.Random(seed * 7919 + s)
+        kind = s % 4
+        if kind == 0:
+            rows.append(gen.hurdle_rich_perm(n, seed * 7919 + s))
+        elif kind == 1:
+            rows.append(gen.random_signed_perm(n, rng))
+        elif kind == 2:
+            rows.append(gen.k_reversal_perm(n, rng.randrange(1, 10), rng))
+        else:
+            p = gen.hurdle_rich_perm(n, seed * 7919 + s)
+            q = gen.random_signed_perm(n, rng)
+            rows.append([(q[abs(x) - 1] if x > 0 else -q[abs(x) - 1]) for x in p])
+    return np.asarray(rows, dtype=np.int32)
+
+
+def parse_genomes(path):
+    """Minimal reader of the `>name / genes / $` format for unichromosomal fixtures
+    (names, int32 table); comments and `$ ; ( ) { }` are skipped."""
+    names, rows, cur = [], [], None
+    with open(path) as f:
+        for line in f:
+            line = line.split("#", 1)[0].strip()
+            if not line:
+                continue
+            if line.startswith(">"):
+                names.append(line[1:])
+                cur = []
+                rows.append(cur)
+                continue
+            for tok in line.replace("$", " ").replace(";", " ").split():
+                cur.append(int(tok))
+    return names, np.asarray(rows, dtype=np.int32)
+
+
+def run_cli(binary, args, cwd):
+    import subprocess
+    r = subprocess.run([binary] + list(args), cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    return r.returncode, r.stdout.decode(), r.stderr.decode()
+
+
+def normalise_report(text: str) -> str:
+    """Drop the two header lines that echo argv[0] and the input path."""
+    keep = [ln for ln in text.splitlines() if not ln.startswith("Running:")]
+    return "\n".join(keep) + ("\n" if text.endswith("\n") else "")
+
+
+def error_head(err: str) -> str:
+    """The reference prints its error text, then a blank line and the usage screen: keep the text."""
+    return err.split("\n\nGRIMM", 1)[0].rstrip("\n")

@@ -1,0 +1,94 @@
+"""GPU parity tests of the scenario search, through the C ABI, against oracle and golden vectors."""
+import json
+import random
+
+import numpy as np
+import pytest
+
+import _util as U
+from grsr_b200 import capi, gen
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_pairs(srcs, dsts):
+    got = capi.scenario_batch(np.asarray(srcs, dtype=np.int32), np.asarray(dsts, dtype=np.int32))
+    for s, d, steps in zip(srcs, dsts, got):
+        want, _ = U.orc_scenario(s, d)
+        assert np.array_equal(steps, want), (list(s), list(d))
+        assert np.array_equal(U.apply_steps(s, steps), np.asarray(d))
+
+
+def test_golden_reference_scenarios():
+    cases = json.load(open(U.GOLDEN + "/scenarios_mixed.json"))
+    by_n = {}
+    for c in cases:
+        by_n.setdefault(len(c["src"]), []).append(c)
+    for n, cs in by_n.items():
+        got = capi.scenario_batch(np.array([c["src"] for c in cs], dtype=np.int32),
+                                  np.array([c["dst"] for c in cs], dtype=np.int32))
+        for c, steps in zip(cs, got):
+            assert steps.tolist() == c["steps"]
+
+
+def test_published_docx_scenarios():
+    """The three worked scenarios printed in the paper supplement (Additional_file_2.docx)."""
+    for c in json.load(open(U.GOLDEN + "/docx_scenarios.json")):
+        src, dst = c["source"], c["destination"]
+        steps = capi.scenario_batch(src, dst)[0]
+        assert len(steps) == len(c["step_values"])
+        cur = np.array(src)
+        for (s, e), (sv, ev), row in zip(steps, c["step_values"], c["rows"][1:]):
+            assert (cur[s], cur[e]) == (sv, ev)
+            cur[s:e + 1] = -cur[s:e + 1][::-1]
+            assert cur.tolist() == row
+
+
+def test_example_config1_scenarios():
+    g = U.orc_circular_align(U.parse_genomes(U.EXAMPLE)[1])
+    srcs, dsts = [g[0], g[0], g[1]], [g[1], g[2], g[2]]
+    got = capi.scenario_batch(np.array(srcs), np.array(dsts))
+    assert [len(x) for x in got] == [20, 12, 15]
+    assert got[0][0].tolist() == [3, 3] and got[0][-1].tolist() == [5, 24]
+    _check_pairs(srcs, dsts)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 33, 64, 100, 200])
+def test_mixed_pairs(n):
+    srcs, dsts = [], []
+    for s in range(16):
+        seed = n * 100 + s
+        rng = random.Random(seed)
+        kind = s % 4
+        if kind == 0:
+            src, dst = gen.random_signed_perm(n, rng), gen.random_signed_perm(n, rng)
+        elif kind == 1:
+            src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
+        elif kind == 2:
+            src, dst = list(range(1, n + 1)), gen.hurdle_rich_perm(n, seed)
+        else:
+            src = gen.k_reversal_perm(n, rng.randrange(1, 8), rng)
+            dst = gen.k_reversal_perm(n, rng.randrange(0, 5), rng)
+        srcs.append(src)
+        dsts.append(dst)
+    _check_pairs(srcs, dsts)
+
+
+def test_random_n1000_and_round_trip_n5000():
+    rng = random.Random(5)
+    src, dst = gen.random_signed_perm(1000, rng), list(range(1, 1001))
+    _check_pairs([src], [dst])
+    # size-independent property at config-4 size: the scenario has exactly d steps and sorts
+    srcs = np.array([gen.random_signed_perm(5000, rng) for _ in range(4)], dtype=np.int32)
+    dsts = np.array([gen.random_signed_perm(5000, rng) for _ in range(4)], dtype=np.int32)
+    got = capi.scenario_batch(srcs, dsts)
+    for k in range(4):
+        g = np.stack([srcs[k], dsts[k]])
+        d = capi.dist_pairs(g, [[0, 1]])[0]
+        assert len(got[k]) == d
+        assert np.array_equal(U.apply_steps(srcs[k], got[k]), dsts[k])
+
+
+def test_identical_genomes_have_empty_scenario():
+    p = list(range(1, 41))
+    assert len(capi.scenario_batch(p, p)[0]) == 0
