@@ -32,6 +32,7 @@ SIGNATURES = {
     "grsr_last_error": (ctypes.c_char_p, []),
     "grsr_device_count": (ctypes.c_int, []),
     "grsr_max_genes": (ctypes.c_int, []),
+    "grsr_release": (None, []),
     "grsr_dist_pairs": (ctypes.c_int, [I32P, ctypes.c_int, ctypes.c_int, I32P, ctypes.c_int64, I32P,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "grsr_dist_matrix": (ctypes.c_int, [I32P, ctypes.c_int, ctypes.c_int, I32P, ctypes.c_int, ctypes.c_int]),
@@ -84,6 +85,17 @@ def device_count() -> int:
 
 def max_genes() -> int:
     return lib().grsr_max_genes()
+
+
+def release() -> None:
+    lib().grsr_release()
+
+
+def triangle_pairs(G: int) -> np.ndarray:
+    """Pair list of the upper triangle in the library's flat order: column by column,
+    (0,1), (0,2), (1,2), (0,3), ... (pair (i,j), i<j, has index j(j-1)/2 + i)."""
+    j, i = np.tril_indices(G, k=-1)
+    return np.stack([i, j], axis=1).astype(np.int32)
 
 
 def dist_pairs(genomes, pairs, stats: bool = False, first_device: int = 0, ngpus: int = 1) -> np.ndarray:

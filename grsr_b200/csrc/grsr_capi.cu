@@ -57,56 +57,57 @@ int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-// threads per block for the one-pair-per-block kernels: enough lanes to cover the 2n+2 vertices a
-// few times per pass, small enough that several blocks stay resident per SM.
-int pick_threads(int n) {
-  int t = env_int("GRSR_THREADS", 0);
-  if (t >= 32 && t <= 256 && (t % 32) == 0) return t;
-  int size = 2 * n + 2;
-  if (size <= 128) return 32;
-  if (size <= 512) return 64;
-  if (size <= 2048) return 128;
-  return 256;
-}
+struct Launch { int threads; int ept; int grid; size_t smem; };
 
-struct Launch { int threads; int grid; size_t smem; };
-
+// Shape, shared memory and grid of a one-pair-per-block kernel instance `kernel` (already
+// specialised for L.ept): opt in to the large carve-out, ask the occupancy calculator how many
+// blocks stay resident per SM and launch a whole number of resident waves (148 SMs x occupancy).
 template <class K>
-int plan_launch(K kernel, int n, bool keep_orbits, long long units, Launch &L) {
+int finish_plan(K kernel, long long units, Launch &L) {
   int dev;
   CK(cudaGetDevice(&dev));
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  L.smem = grsr::work_bytes(n, keep_orbits);
-  if (n > grsr::kMaxSmemGenes || L.smem > (size_t)di.smem_optin || 2 * n + 2 > 65535)
-    return fail(GRSR_ERR_TOOLARGE,
-                "num_genes=%d needs %zu bytes of shared memory per pair; this build keeps the "
-                "breakpoint graph on chip and accepts at most %d genes",
-                n, L.smem, grsr_max_genes());
-  L.threads = pick_threads(n);
+  if (L.smem > (size_t)di.smem_optin)
+    return fail(GRSR_ERR_TOOLARGE, "%zu bytes of shared memory per pair exceed the device limit %d",
+                L.smem, di.smem_optin);
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          (int)cudaSharedmemCarveoutMaxShared));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, L.threads, L.smem));
   if (occ < 1) return fail(GRSR_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", L.smem);
-  occ = env_int("GRSR_OCC", occ) < occ ? env_int("GRSR_OCC", occ) : occ;
-  long long g = (long long)di.sms * occ;   // a whole number of resident waves: 148 SMs x occupancy
+  int cap = env_int("GRSR_OCC", occ);
+  if (cap >= 1 && cap < occ) occ = cap;
+  long long g = (long long)di.sms * occ;
   if (g > units) g = units;
   if (g < 1) g = 1;
   L.grid = (int)g;
   return GRSR_OK;
 }
 
+int check_genes_fit(int n, bool scenario) {
+  int lim = scenario ? grsr_max_genes() : grsr::kMaxSmemGenes;
+  if (n > lim)
+    return fail(GRSR_ERR_TOOLARGE,
+                "num_genes=%d: this build keeps the breakpoint graph in shared memory and accepts at "
+                "most %d genes for %s", n, lim, scenario ? "scenarios" : "distances");
+  return GRSR_OK;
+}
+
+// Upper triangle enumerated column by column -- (0,1), (0,2), (1,2), (0,3), ... -- so that
+// consecutive pairs share their pi row (the one whose signed inverse the kernel keeps staged):
+// pair p = (i, j) with p = j(j-1)/2 + i, i < j.
 __global__ void triangle_pairs_kernel(int G, long long first, long long count, int32_t *pairs) {
   long long stride = (long long)gridDim.x * blockDim.x;
+  (void)G;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < count; q += stride) {
     long long p = first + q;
-    double t = 2.0 * G - 1.0;
-    long long i = (long long)((t - sqrt(t * t - 8.0 * (double)p)) * 0.5);
-    if (i < 0) i = 0;
-    while (i > 0 && i * (2LL * G - i - 1) / 2 > p) i--;
-    while ((i + 1) * (2LL * G - (i + 1) - 1) / 2 <= p) i++;
-    long long j = i + 1 + (p - i * (2LL * G - i - 1) / 2);
+    long long j = (long long)((1.0 + sqrt(1.0 + 8.0 * (double)p)) * 0.5);
+    while (j * (j - 1) / 2 > p) j--;
+    while ((j + 1) * j / 2 <= p) j++;
+    long long i = p - j * (j - 1) / 2;
     pairs[2 * q] = (int32_t)i; pairs[2 * q + 1] = (int32_t)j;
   }
 }
@@ -163,6 +164,31 @@ struct DevBuf {
   }
 };
 
+// Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
+// survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
+// 20 MB around it would cost as much again).  One call at a time per device (mutex).
+struct DevCache {
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  void *buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t cap[4] = {0, 0, 0, 0};
+};
+const int kMaxDevices = 64;
+DevCache g_cache[kMaxDevices];
+
+int cache_reserve(DevCache &c, int slot, size_t bytes, void **out) {
+  if (c.cap[slot] < bytes) {
+    if (c.buf[slot]) { cudaFree(c.buf[slot]); c.buf[slot] = nullptr; c.cap[slot] = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&c.buf[slot], want);
+    if (e != cudaSuccess)
+      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    c.cap[slot] = want;
+  }
+  *out = c.buf[slot];
+  return GRSR_OK;
+}
+
 enum PairSource { PAIRS_LIST, PAIRS_TRIANGLE, PAIRS_SQUARE };
 
 // One device's share of a pair job: copy the genome table in, build the signed inverses, obtain the
@@ -171,44 +197,38 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
                         const int32_t *pairs_host, long long first, long long count,
                         int32_t *out_host, int stride) {
   if (count <= 0) return GRSR_OK;
+  if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
-  cudaStream_t st;
-  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  DevBuf dg, ds, dp, dout;
+  DevCache &c = g_cache[dev];
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t st = c.stream;
   size_t gbytes = (size_t)G * n * sizeof(int32_t);
+  void *dg, *ds, *dp, *dout;
   int rc;
-  if ((rc = dg.alloc(gbytes)) || (rc = ds.alloc(gbytes)) ||
-      (rc = dp.alloc((size_t)count * 2 * sizeof(int32_t))) ||
-      (rc = dout.alloc((size_t)count * stride * sizeof(int32_t)))) {
-    cudaStreamDestroy(st);
+  if ((rc = cache_reserve(c, 0, gbytes, &dg)) || (rc = cache_reserve(c, 1, gbytes, &ds)) ||
+      (rc = cache_reserve(c, 2, (size_t)count * 2 * sizeof(int32_t), &dp)) ||
+      (rc = cache_reserve(c, 3, (size_t)count * stride * sizeof(int32_t), &dout)))
     return rc;
+  CK(cudaMemcpyAsync(dg, genomes, gbytes, cudaMemcpyHostToDevice, st));
+  if ((rc = grsr_signed_inverse_dev((const int32_t *)dg, G, n, (int32_t *)ds, st))) return rc;
+  if (src == PAIRS_LIST) {
+    CK(cudaMemcpyAsync(dp, pairs_host + 2 * first, (size_t)count * 2 * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, st));
+  } else if (src == PAIRS_TRIANGLE) {
+    if ((rc = grsr_triangle_pairs_dev(G, first, count, (int32_t *)dp, st))) return rc;
+  } else {
+    int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
+    square_pairs_kernel<<<blocks, 256, 0, st>>>(G, first, count, (int32_t *)dp);
+    CK(cudaGetLastError());
   }
-  auto body = [&]() -> int {
-    CK(cudaMemcpyAsync(dg.p, genomes, gbytes, cudaMemcpyHostToDevice, st));
-    int r = grsr_signed_inverse_dev((const int32_t *)dg.p, G, n, (int32_t *)ds.p, st);
-    if (r) return r;
-    if (src == PAIRS_LIST) {
-      CK(cudaMemcpyAsync(dp.p, pairs_host + 2 * first, (size_t)count * 2 * sizeof(int32_t),
-                         cudaMemcpyHostToDevice, st));
-    } else if (src == PAIRS_TRIANGLE) {
-      r = grsr_triangle_pairs_dev(G, first, count, (int32_t *)dp.p, st);
-      if (r) return r;
-    } else {
-      int blocks = (int)((count + 255) / 256 < 1184 ? (count + 255) / 256 : 1184);
-      square_pairs_kernel<<<blocks, 256, 0, st>>>(G, first, count, (int32_t *)dp.p);
-      CK(cudaGetLastError());
-    }
-    r = grsr_dist_pairs_dev((const int32_t *)dg.p, (const int32_t *)ds.p, n, (const int32_t *)dp.p,
-                            count, (int32_t *)dout.p, stride, st);
-    if (r) return r;
-    CK(cudaMemcpyAsync(out_host, dout.p, (size_t)count * stride * sizeof(int32_t),
-                       cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return GRSR_OK;
-  };
-  rc = body();
-  cudaStreamDestroy(st);
-  return rc;
+  if ((rc = grsr_dist_pairs_dev((const int32_t *)dg, (const int32_t *)ds, n, (const int32_t *)dp,
+                                count, (int32_t *)dout, stride, st)))
+    return rc;
+  CK(cudaMemcpyAsync(out_host, dout, (size_t)count * stride * sizeof(int32_t),
+                     cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GRSR_OK;
 }
 
 // Split [0, total) into ngpus contiguous slices, one host thread per device; no data-path collective.
@@ -243,19 +263,12 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  size_t smem = grsr::work_bytes(n, true) + grsr::scen_extra_bytes(n);
-  if (n > grsr_max_genes() || smem > (size_t)di.smem_optin)
-    return fail(GRSR_ERR_TOOLARGE,
-                "num_genes=%d needs %zu bytes of shared memory per scenario; this build accepts at "
-                "most %d genes", n, smem, grsr_max_genes());
-  int threads = pick_threads(n);
-  CK(cudaFuncSetAttribute(grsr::scenario_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, grsr::scenario_kernel, threads, smem));
-  if (occ < 1) return fail(GRSR_ERR_CUDA, "scenario kernel does not fit on an SM");
-  long long grid = (long long)di.sms * occ;
-  if (grid > npairs) grid = npairs;
+  if ((rc = check_genes_fit(n, true))) return rc;
+  Launch L;
+  grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+  L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
+  GRSR_DISPATCH_EPT(L.ept, rc = finish_plan(grsr::scenario_kernel<kEpt>, npairs, L));
+  if (rc) return rc;
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   DevBuf dsrc, ddst, dsteps, dns, dstat, dtick;
@@ -272,9 +285,9 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
     CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(dtick.p, 0, 4, st));
-    grsr::scenario_kernel<<<(int)grid, threads, smem, st>>>(
+    GRSR_DISPATCH_EPT(L.ept, (grsr::scenario_kernel<kEpt><<<L.grid, L.threads, L.smem, st>>>(
         (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
-        (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p);
+        (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(steps, dsteps.p, sbytes, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nsteps, dns.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
@@ -310,11 +323,28 @@ int grsr_device_count(void) {
   return cnt;
 }
 
+void grsr_release(void) {
+  for (int d = 0; d < kMaxDevices; d++) {
+    DevCache &c = g_cache[d];
+    std::lock_guard<std::mutex> lk(c.mu);
+    bool any = c.stream != nullptr;
+    for (int k = 0; k < 4; k++) any = any || c.buf[k];
+    if (!any) continue;
+    if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
+    for (int k = 0; k < 4; k++) { if (c.buf[k]) cudaFree(c.buf[k]); c.buf[k] = nullptr; c.cap[k] = 0; }
+    if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
+  }
+}
+
 int grsr_max_genes(void) {
   int n = grsr::kMaxSmemGenes;
-  while (n > 1 && (grsr::work_bytes(n, true) + grsr::scen_extra_bytes(n) > 227u * 1024u ||
-                   2 * n + 2 > 65535))
-    n--;
+  for (; n > 1; n--) {
+    int t, e;
+    grsr::pick_shape(n, 0, &t, &e);
+    if (t * e >= 2 * n + 2 &&
+        grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n) <= 227u * 1024u)
+      break;
+  }
   return n;
 }
 
@@ -344,11 +374,15 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   if (npairs <= 0) return GRSR_OK;
   if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
   if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
-  Launch L;
-  int rc = plan_launch(grsr::dist_pairs_kernel, num_genes, false, npairs, L);
+  int rc = check_genes_fit(num_genes, false);
   if (rc) return rc;
-  grsr::dist_pairs_kernel<<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
-      d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride);
+  Launch L;
+  grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+  L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+  GRSR_DISPATCH_EPT(L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kEpt>, npairs, L));
+  if (rc) return rc;
+  GRSR_DISPATCH_EPT(L.ept, (grsr::dist_pairs_kernel<kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
+      d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
   CK(cudaGetLastError());
   return GRSR_OK;
 }
@@ -398,9 +432,9 @@ int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes, int
   }
   // host gather of matrix rows: distmatrix[i][j] = distmatrix[j][i] (G/uniinvdist.c:84-88)
   long long p = 0;
-  for (long long i = 0; i < G; i++) {
-    distmatrix[i * G + i] = 0;
-    for (long long j = i + 1; j < G; j++, p++)
+  for (long long j = 0; j < G; j++) {
+    distmatrix[j * G + j] = 0;
+    for (long long i = 0; i < j; i++, p++)
       distmatrix[i * G + j] = distmatrix[j * G + i] = flat[p];
   }
   return GRSR_OK;

@@ -1,24 +1,23 @@
 // grsr_core.cuh -- device code of the reversal-distance hot path (sm_100a).
 //
 // One thread block owns one permutation pair (gamma, pi) and keeps that pair's whole breakpoint
-// graph in shared memory; many pairs are processed per launch (grid-stride over the pair list).
-// What it reproduces, bit for bit, is the reference GRIMM 2.01 pipeline invdist_noncircular_G
-// (reference G/uniinvdist.c:150-214):
+// graph in shared memory; a launch processes many pairs (each block walks a contiguous chunk of the
+// pair list).  What it reproduces, bit for bit, is the reference GRIMM 2.01 pipeline
+// invdist_noncircular_G (reference G/uniinvdist.c:150-214):
 //
 //   reference stage (file:line)                           here
 //   ---------------------------------------------------   -----------------------------------------
-//   double_perms            G/graph_edit.c:46-157          phase 1 (signed relative permutation rho)
-//   buildG_grey             G/mcrdist.c:116-145            phase 2 (grey[v] = where[perm[v]^1])
-//   classify_cycle_path     G/graph_edit.c:207-457         phase 3 (pointer jumping) + phase 4
+//   double_perms            G/graph_edit.c:46-157          phase A: grey edges written straight from
+//   buildG_grey             G/mcrdist.c:116-145              the signed positions of gamma's genes in pi
+//   num_breakpoints         G/uniinvdist.c:124-142         phase A (adjacency count)
+//   classify_cycle_path     G/graph_edit.c:207-457         phase B (pointer jumping) + phase C
+//   classify_connected_c.   G/graph_components.c:257-336   orientation bit carried by phase B / S6
 //   form_connected_comp.    G/graph_components.c:50-242    slow path S1-S5 (extent queries + union-find)
-//   classify_connected_c.   G/graph_components.c:257-336   phase 4b / S6
 //   calc_num_hurdles_and_f. G/graph_components.c:465-727   slow path S7-S9
-//   num_breakpoints         G/uniinvdist.c:124-142         phase 2 (adjacency count)
 //
 // The sequential walks and the stack sweep of the reference are replaced by data-parallel
-// formulations (see DESIGN.md section 3 for the equivalence arguments); the numbers produced are
-// the same.  All arithmetic is 32-bit integer; vertex ids are stored as 16-bit in shared memory
-// (2n+2 <= 65535).
+// formulations (DESIGN.md section 3 gives the equivalence arguments); the numbers produced are the
+// same.  All arithmetic is 32-bit integer; vertex ids fit 15 bits in shared memory (2n+2 <= 32767).
 //
 // The file is also compiled by g++ against tests/emu/cuda_emu.hpp (a SIMT emulator used only by
 // the CPU test-suite to debug kernel logic); nothing in the product selects that build.
@@ -36,40 +35,54 @@ namespace grsr {
 typedef uint16_t vid_t;
 static const unsigned kNone = 0xFFFFu;
 static const unsigned kFull = 0xFFFFFFFFu;
-static const int kMaxSmemGenes = 14000;   // 2n+2 vertices * ~10 B must fit 227 KB of shared memory
+static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex within 227 KB smem
+
+// Jumping word of vertex v:  [31:17] label = smallest vertex seen on v's sigma-orbit window,
+//                            [16]    1 if an oriented grey edge was seen on that window,
+//                            [15]    1 if v is an end of an adjacency (then sigma(v) = v),
+//                            [14:0]  next = end of the window (sigma^k(v)).
+#define GRSR_W_LABEL(w) ((w) >> 17)
+#define GRSR_W_NEXT(w) ((w) & 0x7FFFu)
+#define GRSR_W_ORBIT 0x10000u
+#define GRSR_W_ADJ 0x8000u
 
 struct Stats { int d, b, c, h, f; };
 
-// Shared-memory workspace of one pair.  S = 2n+2 vertices, padded to Sp (multiple of 8).
+// Shared-memory workspace of one pair.  S = 2n+2 vertices, padded to Sp = a multiple of the
+// block's slots (threads x words per thread, see dist_core) so that no bounds checks are needed.
 struct Work {
-  uint32_t *W;              // [Sp] pointer-jumping words (label<<16 | next); later per-root scratch
-  vid_t *A1;                // [Sp] perm -> grey partner -> per-root links -> compacted lists
-  vid_t *A2;                // [Sp] value->position -> cycle id -> compacted lists
-  vid_t *ORB;               // [Sp] sigma-orbit label per vertex (scenario kernels only)
+  uint32_t *W;              // [Sp] jumping words; later per-root scratch of the slow path
+  vid_t *A1;                // [S]  slow path: per-root flags/links, then compacted lists
+  vid_t *A2;                // [S]  slow path: cycle id per vertex, then compacted lists
+  vid_t *ORB;               // [S]  sigma-orbit label per vertex (scenario kernels only)
   vid_t *BLK;               // [2*NB] per-32-vertex block: min cycle id, max cycle reach
   unsigned long long *red;  // [34] reduction scratch
   int S, Sp, NB;
 };
 
-__host__ __device__ inline int padded_size(int n) { return (2 * n + 2 + 7) & ~7; }
+__host__ __device__ inline int padded_size(int n, int slots) {
+  int s = 2 * n + 2;
+  return ((s + slots - 1) / slots) * slots;
+}
 __host__ __device__ inline int num_vblocks(int n) { return (2 * n + 2 + 31) >> 5; }
 
-__host__ __device__ inline size_t work_bytes(int n, bool keep_orbits) {
-  size_t sp = (size_t)padded_size(n);
-  size_t b = sp * 4 + sp * 2 + sp * 2 + (keep_orbits ? sp * 2 : 0);
+// slots = threads per block x words per thread (a multiple of 32); only W is padded to it
+__host__ __device__ inline size_t work_bytes(int n, int slots, bool keep_orbits) {
+  size_t sp = (size_t)padded_size(n, slots), sv = (size_t)((2 * n + 2 + 7) & ~7);
+  size_t b = sp * 4 + sv * 2 + sv * 2 + (keep_orbits ? sv * 2 : 0);
   b += (((size_t)num_vblocks(n) * 2 * sizeof(vid_t)) + 15) & ~(size_t)15;
   b += 34 * sizeof(unsigned long long);
   return b;
 }
 
-__device__ inline void work_carve(Work &wk, unsigned char *base, int n, bool keep_orbits) {
-  int sp = padded_size(n);
+__device__ inline void work_carve(Work &wk, unsigned char *base, int n, int slots, bool keep_orbits) {
+  int sp = padded_size(n, slots), sv = (2 * n + 2 + 7) & ~7;
   wk.S = 2 * n + 2; wk.Sp = sp; wk.NB = num_vblocks(n);
   wk.W = (uint32_t *)base;  base += (size_t)sp * 4;
-  wk.A1 = (vid_t *)base;    base += (size_t)sp * 2;
-  wk.A2 = (vid_t *)base;    base += (size_t)sp * 2;
+  wk.A1 = (vid_t *)base;    base += (size_t)sv * 2;
+  wk.A2 = (vid_t *)base;    base += (size_t)sv * 2;
   wk.ORB = keep_orbits ? (vid_t *)base : (vid_t *)0;
-  if (keep_orbits) base += (size_t)sp * 2;
+  if (keep_orbits) base += (size_t)sv * 2;
   wk.BLK = (vid_t *)base;   base += (((size_t)wk.NB * 2 * sizeof(vid_t)) + 15) & ~(size_t)15;
   wk.red = (unsigned long long *)base;
 }
@@ -149,8 +162,8 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
 // --------------------------------------------------------------------------------------------------
 // Hurdles and fortress for a graph that has at least one unoriented cycle.
 // Entry state: A2[v] = cycle id (leftmost vertex) or kNone for adjacency vertices;
-//              W[r] = 1 if cycle r (r = its leftmost vertex, always even) owns an oriented grey
-//              edge, else 0; W[odd] = 0.  A1 is free.
+//              W[v] = converged jumping word of v (bit 16 = v's cycle owns an oriented grey edge).
+//              A1 is free.
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
 __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
@@ -163,7 +176,7 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
   //     reach (W[r+1] = rightmost vertex of cycle r, filled by S2).
   for (int k = tid; k <= n; k += nt) {
     unsigned a = 2u * k;
-    if (A2[a] == a) { A1[a] = (vid_t)W[a]; W[a] = a; W[a + 1] = 0; }
+    if (A2[a] == a) { A1[a] = (vid_t)((W[a] >> 16) & 1u); W[a] = a; W[a + 1] = 0; }
   }
   __syncthreads();
 
@@ -345,100 +358,92 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
 }
 
 // --------------------------------------------------------------------------------------------------
-// dist_core: full invdist_noncircular_G for the pair described by rho, where
-//   rho(i) in +-(1..n) = signed position in gamma of the gene at position i of pi
-// (perm[2i+1], perm[2i+2] of the reference follow from it, G/graph_edit.c:69-116).
+// dist_core: full invdist_noncircular_G for the pair described by inv, where
+//   inv(t) in +-(1..n), t in [0, n) = signed position in pi of the t-th gene of gamma
+// (sign = relative orientation).  Vertices are the doubled positions of pi, 0..2n+1, exactly the
+// reference's numbering: gene at position p owns vertices 2p+1 (left end) and 2p+2 (right end) when
+// it reads forward, swapped when it reads backward; black edges join (2k, 2k+1).  Grey edge t
+// (t = 0..n) joins the right end of gamma's gene t-1 (vertex 0 for t = 0) to the left end of
+// gamma's gene t (vertex 2n+1 for t = n) -- which is what perm / invperm / greyEdges of the
+// reference encode (G/graph_edit.c:69-145, G/mcrdist.c:116-145).
+//
+// EPT = jumping words kept in registers per thread; blockDim.x * EPT == wk.Sp.
 // kKeepOrbits additionally leaves in wk.ORB[v] the sigma-orbit label of every vertex
 // (sigma(v) = grey[v^1]; kNone for the two ends of an adjacency); two breakpoint vertices x, y have
 // an even graphdist (G/graph_edit.c:1165-1238) exactly when ORB[x] == ORB[y].
 // All threads of the block must call; all receive the result.
 // --------------------------------------------------------------------------------------------------
-template <bool kKeepOrbits, class RhoFn>
-__device__ inline Stats dist_core(Work &wk, int n, RhoFn rho) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+template <int EPT, bool kKeepOrbits, class InvFn>
+__device__ inline Stats dist_core(Work &wk, int n, InvFn inv) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int S = wk.S;
-  uint32_t *W = wk.W; vid_t *A1 = wk.A1, *A2 = wk.A2;
-  uint32_t *A1w = (uint32_t *)A1, *A2w = (uint32_t *)A2;
+  uint32_t *W = wk.W;
 
-  // phase 1: doubled relative permutation (A1 = perm) and its inverse (A2 = where)
-  for (int i = tid; i < n; i += nt) {
-    int r = rho(i);
-    unsigned a = (r > 0) ? (unsigned)(2 * r - 1) : (unsigned)(-2 * r);
-    unsigned b = (r > 0) ? (unsigned)(2 * r) : (unsigned)(-2 * r - 1);
-    unsigned p = 2u * i + 1u;
-    A1[p] = (vid_t)a; A1[p + 1] = (vid_t)b;
-    A2[a] = (vid_t)p; A2[b] = (vid_t)(p + 1);
-  }
-  if (tid == 0) { A1[0] = 0; A2[0] = 0; A1[S - 1] = (vid_t)(S - 1); A2[S - 1] = (vid_t)(S - 1); }
-  __syncthreads();
-
-  // phase 2: grey partner of v = where[perm[v] ^ 1]; an edge whose partner is its black neighbour
-  // is an adjacency (G/mcrdist.c:125-141).  sigma(v) = grey[v ^ 1] seeds the jumping words.
+  // phase A: one lane per grey edge t.  x = right end of gene t-1, y = left end of gene t.
+  // sigma(x^1) = y and sigma(y^1) = x seed the jumping words; the edge is an adjacency when x and
+  // y are the two ends of one black edge (G/mcrdist.c:135-140) and oriented when x and y have the
+  // same parity (G/graph_components.c:324-329).
   unsigned nadj = 0;
-  for (int k = tid; k <= n; k += nt) {
-    unsigned a = 2u * k;
-    uint32_t pr = A1w[k];
-    unsigned ga = A2[(pr & 0xFFFFu) ^ 1u], gb = A2[(pr >> 16) ^ 1u];
-    if (ga == a + 1) {
-      A1w[k] = 0xFFFFFFFFu;
-      W[a] = (a << 16) | a; W[a + 1] = ((a + 1) << 16) | (a + 1);
-      nadj++;
-    } else {
-      A1w[k] = ga | (gb << 16);
-      W[a] = (a << 16) | gb; W[a + 1] = ((a + 1) << 16) | ga;
+  for (int base = tid & ~31; base <= n; base += nt) {
+    int t = base + lane;
+    int q = (t < n) ? inv(t) : 0;
+    int qp = __shfl_up_sync(kFull, q, 1);
+    if (lane == 0 && t > 0 && t <= n) qp = inv(t - 1);
+    if (t <= n) {
+      unsigned x, y;
+      if (t == 0) x = 0;
+      else { unsigned p = (unsigned)(qp > 0 ? qp : -qp) - 1u; x = (qp > 0) ? 2u * p + 2u : 2u * p + 1u; }
+      if (t == n) y = (unsigned)S - 1u;
+      else { unsigned p = (unsigned)(q > 0 ? q : -q) - 1u; y = (q > 0) ? 2u * p + 1u : 2u * p + 2u; }
+      unsigned ob = (((x ^ y) & 1u) == 0u) ? GRSR_W_ORBIT : 0u;
+      unsigned xb = x ^ 1u, yb = y ^ 1u;
+      unsigned ab = (xb == y) ? GRSR_W_ADJ : 0u;
+      nadj += (xb == y);
+      W[xb] = (xb << 17) | ob | ab | y;
+      W[yb] = (yb << 17) | ob | ab | x;
+    }
+  }
+  for (int v = S + tid; v < wk.Sp; v += nt) W[v] = ((unsigned)v << 17) | (unsigned)v;  // padding: self-loops
+  __syncthreads();
+
+  // phase B: pointer jumping along sigma with min-label and or-flag, in place.  Each word is one
+  // atomic 32-bit (label, flag, next) snapshot, so after round r every word covers >= 2^r
+  // successors; stop after ceil(log2(n+1)) rounds or as soon as a whole round changed nothing in
+  // the upper halves.  A thread keeps its EPT words in registers and only reads its successors.
+  {
+    uint32_t R[EPT];
+#pragma unroll
+    for (int j = 0; j < EPT; j++) R[j] = W[tid + j * nt];
+    const int rounds = ceil_log2(n + 1);
+    for (int r = 0; r < rounds; r++) {
+      uint32_t chg = 0;
+#pragma unroll
+      for (int j = 0; j < EPT; j++) {
+        uint32_t w = R[j];
+        uint32_t wu = W[GRSR_W_NEXT(w)];
+        uint32_t nw = (min(w >> 17, wu >> 17) << 17) | ((w | wu) & GRSR_W_ORBIT) | (wu & 0xFFFFu);
+        chg |= (nw ^ w);
+        W[tid + j * nt] = nw;
+        R[j] = nw;
+      }
+      if (!__syncthreads_or((chg >> 16) != 0)) break;
     }
   }
   __syncthreads();
 
-  // phase 3: pointer jumping along sigma with min-label, in place.  Each word is one atomic
-  // 32-bit (label, next) snapshot, so after round r every label covers >= 2^r successors; stop
-  // after ceil(log2(n+1)) rounds or as soon as a whole round changed no label.
-  const int rounds = ceil_log2(n + 1);
-  for (int r = 0; r < rounds; r++) {
-    int changed = 0;
-    for (int v = tid; v < S; v += nt) {
-      uint32_t w = W[v];
-      unsigned u = w & 0xFFFFu;
-      if (u == (unsigned)v) continue;
-      uint32_t wu = W[u];
-      unsigned lab = min(w >> 16, wu >> 16);
-      uint32_t nw = (lab << 16) | (wu & 0xFFFFu);
-      if (nw != w) { W[v] = nw; changed |= (lab != (w >> 16)); }
-    }
-    if (!__syncthreads_or(changed)) break;
-  }
-
-  // phase 4a: cycle id = min of the two orbit labels of a black edge's ends (kNone for an
-  // adjacency); a black edge whose left end is its own cycle id is a cycle root -> count cycles.
-  unsigned ncyc = 0;
+  // phase C: per black edge k = (2k, 2k+1): adjacency flag from the word; cycle id = min of the two
+  // orbit labels; the edge whose left end is its own cycle id is the cycle's root -> count cycles
+  // and the roots whose orbit saw no oriented grey edge.
+  unsigned ncyc = 0, nun = 0;
   for (int k = tid; k <= n; k += nt) {
     unsigned a = 2u * k;
-    unsigned la = W[a] >> 16, lb = W[a + 1] >> 16;
-    const bool adj = (A1w[k] == 0xFFFFFFFFu);
+    uint32_t w0 = W[a], w1 = W[a + 1];
+    const bool adj = (w0 & GRSR_W_ADJ) != 0;
+    unsigned la = w0 >> 17, lb = w1 >> 17;
     if (kKeepOrbits) ((uint32_t *)wk.ORB)[k] = adj ? 0xFFFFFFFFu : (la | (lb << 16));
-    unsigned cy = adj ? kNone : min(la, lb);
-    A2w[k] = cy | (cy << 16);
-    ncyc += (cy == a);
-    W[a] = 0; W[a + 1] = 0;
-  }
-  __syncthreads();
-
-  // phase 4b: a grey edge (i, j) is oriented iff j - i is even (G/graph_components.c:324-329);
-  // flag the cycle that owns one.
-  for (int k = tid; k <= n; k += nt) {
-    uint32_t g = A1w[k];
-    if (g != 0xFFFFFFFFu) {
-      unsigned ga = g & 0xFFFFu, gb = g >> 16;
-      if (!(ga & 1u) || (gb & 1u)) W[A2[2 * k]] = 1;
-    }
-  }
-  __syncthreads();
-
-  // phase 4c: unoriented cycles left?  If none every component is oriented: h = f = 0.
-  unsigned nun = 0;
-  for (int k = tid; k <= n; k += nt) {
-    unsigned a = 2u * k;
-    if (A2[a] == a && W[a] == 0) nun++;
+    const bool root = !adj && (min(la, lb) == a);
+    ncyc += root;
+    nun += (root && !(w0 & GRSR_W_ORBIT));
   }
   unsigned long long tot =
       blk_sum_u64(((unsigned long long)nadj << 42) | ((unsigned long long)ncyc << 21) | nun, wk.red);
@@ -447,6 +452,15 @@ __device__ inline Stats dist_core(Work &wk, int n, RhoFn rho) {
   st.c = (int)((tot >> 21) & 0x1FFFFFu);
   st.h = 0; st.f = 0;
   if ((tot & 0x1FFFFFu) != 0) {
+    // some cycle is unoriented: the component analysis is needed.  Cycle ids per vertex first.
+    uint32_t *A2w = (uint32_t *)wk.A2;
+    for (int k = tid; k <= n; k += nt) {
+      unsigned a = 2u * k;
+      uint32_t w0 = W[a], w1 = W[a + 1];
+      unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(w0 >> 17, w1 >> 17);
+      A2w[k] = cy | (cy << 16);
+    }
+    __syncthreads();
     unsigned hf = hurdles_slow_path(wk, n);
     st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
   }
@@ -454,13 +468,13 @@ __device__ inline Stats dist_core(Work &wk, int n, RhoFn rho) {
   return st;
 }
 
-// rho for a pair of rows of the genome table: pi in global memory, the signed inverse of gamma
-// staged in shared memory (sinv[|g|-1] = +-(position+1) of gene |g| in gamma).
-struct RhoFromRows {
-  const int32_t *pi; const int32_t *sinv_sm;
-  __device__ inline int operator()(int i) const {
-    int g = pi[i];
-    int s = sinv_sm[(g > 0 ? g : -g) - 1];
+// inv for a pair of rows of the genome table: gamma in global memory, the signed inverse of pi
+// staged in shared memory (sinv[|g|-1] = +-(position+1) of gene |g| in pi).
+struct InvFromRows {
+  const int32_t *gamma; const int16_t *sinv_pi;
+  __device__ inline int operator()(int t) const {
+    int g = gamma[t];
+    int s = sinv_pi[(g > 0 ? g : -g) - 1];
     return g > 0 ? s : -s;
   }
 };
@@ -479,28 +493,63 @@ __global__ void signed_inverse_kernel(const int32_t *__restrict__ genomes, int32
   }
 }
 
+__host__ __device__ inline size_t stage_bytes(int n) { return (((size_t)n * 2) + 15) & ~(size_t)15; }
+
+// Launch shape of the one-pair-per-block kernels: threads per block and jumping words per thread
+// (EPT, a power of two <= 64) with threads * EPT >= 2n+2.  About 16 words per thread keeps the
+// per-round loop in registers while several blocks stay resident per SM.
+__host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ept) {
+  int S = 2 * n + 2, t = 32;
+  if (forced_threads >= 32 && forced_threads <= 512 && (forced_threads % 32) == 0) t = forced_threads;
+  else while (t < 512 && t * 16 < S) t *= 2;
+  int e = 1;
+  while (e < 64 && t * e < S) e *= 2;
+  *threads = t; *ept = e;
+}
+
+#define GRSR_DISPATCH_EPT(ept, ...)                      \
+  switch (ept) {                                         \
+    case 1:  { constexpr int kEpt = 1;  __VA_ARGS__; } break; \
+    case 2:  { constexpr int kEpt = 2;  __VA_ARGS__; } break; \
+    case 4:  { constexpr int kEpt = 4;  __VA_ARGS__; } break; \
+    case 8:  { constexpr int kEpt = 8;  __VA_ARGS__; } break; \
+    case 16: { constexpr int kEpt = 16; __VA_ARGS__; } break; \
+    case 32: { constexpr int kEpt = 32; __VA_ARGS__; } break; \
+    default: { constexpr int kEpt = 64; __VA_ARGS__; } break; \
+  }
+
 // Batched distance: pair p = (gamma row pairs[2p], pi row pairs[2p+1]) as in setinvmatrix
 // (reference G/uniinvdist.c:80-90).  stride 1: out[p] = d; stride 5: out[5p..] = {d,b,c,h,f}.
-__global__ void __launch_bounds__(256)
+// Block b owns the contiguous pairs [b*chunk, (b+1)*chunk); the signed inverse of pi stays staged in
+// shared memory while consecutive pairs share their pi row.
+template <int EPT>
+__global__ void __launch_bounds__(512, (EPT <= 16) ? 3 : 1)
 dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                   const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                   int stride) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
-  work_carve(wk, smem_raw, n, false);
-  int32_t *stage = (int32_t *)wk.W;
-  for (long long p = blockIdx.x; p < npairs; p += gridDim.x) {
-    const int32_t *sg = sinv + (long long)pairs[2 * p] * n;
-    const int32_t *pi = genomes + (long long)pairs[2 * p + 1] * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = sg[i];
-    __syncthreads();
-    RhoFromRows rho; rho.pi = pi; rho.sinv_sm = stage;
-    Stats st = dist_core<false>(wk, n, rho);
+  const int slots = blockDim.x * EPT;
+  work_carve(wk, smem_raw, n, slots, false);
+  int16_t *stage = (int16_t *)(smem_raw + work_bytes(n, slots, false));
+  const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * chunk;
+  const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
+  int staged = -1;
+  for (long long p = p0; p < p1; p++) {
+    const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
+    if (pj != staged) {
+      const int32_t *sp = sinv + (long long)pj * n;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = (int16_t)sp[i];
+      staged = pj;
+      __syncthreads();
+    }
+    InvFromRows inv; inv.gamma = genomes + (long long)gi * n; inv.sinv_pi = stage;
+    Stats st = dist_core<EPT, false>(wk, n, inv);
     if (threadIdx.x == 0) {
       if (stride == 1) out[p] = st.d;
       else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
     }
-    __syncthreads();
   }
 }
 

@@ -27,7 +27,7 @@ static const unsigned kNoKey = 0xFFFFFFFFu;
 static const int kKeyShift = 14;             // key = (j - i) << 14 | i ; n <= kMaxSmemGenes < 2^14
 
 __host__ __device__ inline size_t scen_arr_bytes(int n) { return (((size_t)n + 2) * 2 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t scen_extra_bytes(int n) { return 4 * scen_arr_bytes(n); }
+__host__ __device__ inline size_t scen_extra_bytes(int n) { return 5 * scen_arr_bytes(n); }
 
 __device__ inline unsigned blk_min_u32(unsigned v, unsigned long long *red) {
   v = __reduce_min_sync(kFull, v);
@@ -45,7 +45,7 @@ __device__ inline unsigned blk_min_u32(unsigned v, unsigned long long *red) {
   return v;
 }
 
-// rho of G0: signed position in the destination of the gene at position i of the current genome
+// rho0(i): signed position in the destination of the gene at position i of the current genome
 struct RhoCurrent {
   const int16_t *cur; const int16_t *sdst;
   __device__ inline int operator()(int i) const {
@@ -55,16 +55,20 @@ struct RhoCurrent {
   }
 };
 
-// rho of the trial evaluation invdist_noncircular(trial, dest) (G/opt_scenario.c:980): signed
-// position in trial = current with [i..j] reversed and negated (G/scenario.c:475-486) of the gene
-// at position t of the destination.  inv0[t] is that gene's signed position in current.
-struct RhoTrial {
-  const int16_t *inv0; int i, j;
+// inv of G0 = graph(gamma = destination, pi = current) (G/opt_scenario.c:229): signed position in
+// the current genome of the destination's t-th gene = the inverse of rho0.
+struct InvG0 {
+  const int16_t *inv0;
+  __device__ inline int operator()(int t) const { return inv0[t]; }
+};
+
+// inv of the trial evaluation invdist_noncircular(trial, dest) (G/opt_scenario.c:980), gamma =
+// trial = current with [i..j] reversed and negated (G/scenario.c:475-486), pi = destination:
+// signed position in the destination of trial's t-th gene.
+struct InvTrial {
+  const int16_t *rho0; int i, j;
   __device__ inline int operator()(int t) const {
-    int q = inv0[t];
-    int p = (q > 0 ? q : -q) - 1;
-    if (p >= i && p <= j) { p = i + j - p; return q > 0 ? -(p + 1) : (p + 1); }
-    return q;
+    return (t >= i && t <= j) ? -(int)rho0[i + j - t] : (int)rho0[t];
   }
 };
 
@@ -74,19 +78,22 @@ struct RhoTrial {
 
 // steps: npairs x max_steps (start, end) pairs; nsteps/status: per pair; evals: per pair number of
 // full trial evaluations (diagnostic, may be null); ticket: zero-initialised work counter.
-__global__ void __launch_bounds__(256)
+template <int EPT>
+__global__ void __launch_bounds__(512, (EPT <= 16) ? 3 : 1)
 scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                 int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                 int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
                 unsigned int *ticket) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
-  work_carve(wk, smem_raw, n, true);
-  unsigned char *extra = smem_raw + work_bytes(n, true);
+  const int slots = blockDim.x * EPT;
+  work_carve(wk, smem_raw, n, slots, true);
+  unsigned char *extra = smem_raw + work_bytes(n, slots, true);
   int16_t *CUR = (int16_t *)extra;
   int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
   int16_t *INV0 = (int16_t *)(extra + 2 * scen_arr_bytes(n));
-  vid_t *BPL = (vid_t *)(extra + 3 * scen_arr_bytes(n));
+  int16_t *RHO0 = (int16_t *)(extra + 3 * scen_arr_bytes(n));
+  vid_t *BPL = (vid_t *)(extra + 4 * scen_arr_bytes(n));
   const vid_t *ORB = wk.ORB;
   const int tid = threadIdx.x, nt = blockDim.x;
   __shared__ int s_pair;
@@ -110,12 +117,15 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
     unsigned long long nevals = 0;
     RhoCurrent rho0; rho0.cur = CUR; rho0.sdst = SDST;
     for (;;) {
-      // inverse of rho0, used to write every trial's rho without touching the genomes again
+      // rho0 and its inverse: G0 and every trial of this step are written from these two arrays
       for (int i = tid; i < n; i += nt) {
         int r = rho0(i);
+        RHO0[i] = (int16_t)r;
         INV0[(r > 0 ? r : -r) - 1] = (int16_t)(r > 0 ? (i + 1) : -(i + 1));
       }
-      const Stats g0 = dist_core<true>(wk, n, rho0);          // G/opt_scenario.c:229
+      __syncthreads();
+      InvG0 ig; ig.inv0 = INV0;
+      const Stats g0 = dist_core<EPT, true>(wk, n, ig);       // G/opt_scenario.c:229
       if (g0.d == 0) break;
       if (ns >= max_steps) { code = GRSR_SCEN_OVERFLOW; break; }
 
@@ -155,8 +165,8 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
         if (best == kNoKey) break;
         const int i = (int)(best & ((1u << kKeyShift) - 1u));
         const int j = i + (int)(best >> kKeyShift);
-        RhoTrial rt; rt.inv0 = INV0; rt.i = i; rt.j = j;
-        const Stats t1 = dist_core<false>(wk, n, rt);         // G/opt_scenario.c:974-986
+        InvTrial it; it.rho0 = RHO0; it.i = i; it.j = j;
+        const Stats t1 = dist_core<EPT, false>(wk, n, it);    // G/opt_scenario.c:974-986
         nevals++;
         if (t1.d == g0.d - 1) { fi = i; fj = j; break; }
         lastkey = best;

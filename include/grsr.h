@@ -56,7 +56,10 @@ typedef struct {
 int grsr_abi_version(void);
 const char *grsr_last_error(void);
 int grsr_device_count(void);           /* number of CUDA devices, 0 if none, never fails */
-int grsr_max_genes(void);              /* largest num_genes the kernels of this build accept */
+int grsr_max_genes(void);              /* largest num_genes the scenario kernels of this build accept
+                                          (distances alone accept up to 14000) */
+void grsr_release(void);               /* frees the device buffers the host-buffer entry points keep
+                                          between calls */
 
 /* ---- host-buffer entry points (what GRIMM's own code would call) ------------------------------ */
 
@@ -75,7 +78,8 @@ int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes,
                      int32_t *distmatrix, int first_device, int ngpus);
 
 /* One shard of the same matrix for multi-process use (one process per GPU): the upper triangle is
- * enumerated row-major as a flat list of P = G(G-1)/2 pairs; shard s of k owns the contiguous range
+ * enumerated column by column -- (0,1), (0,2), (1,2), (0,3), ... i.e. pair (i,j), i<j, has index
+ * j(j-1)/2 + i -- as a flat list of P = G(G-1)/2 pairs; shard s of k owns the contiguous range
  * [P*s/k, P*(s+1)/k).  out receives that range's distances (its length is returned in *count). */
 int grsr_dist_matrix_shard(const int32_t *genomes, int num_genomes, int num_genes,
                            int shard, int num_shards, int32_t *out, int64_t *count, int device);
@@ -106,7 +110,7 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
                         const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
                         void *stream);
 
-/* fills d_pairs[2p], d_pairs[2p+1] for p in [first, first+count) of the row-major upper triangle */
+/* fills d_pairs[2q], d_pairs[2q+1] with pair first+q of the column-by-column upper triangle */
 int grsr_triangle_pairs_dev(int num_genomes, int64_t first, int64_t count, int32_t *d_pairs,
                             void *stream);
 

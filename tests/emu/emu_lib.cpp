@@ -1,6 +1,6 @@
-// emu_lib.cpp -- TEST INFRASTRUCTURE ONLY: runs the kernels of grsr_core.cuh on the CPU through the
-// fiber SIMT emulator (cuda_emu.hpp) so kernel logic can be checked where no GPU exists.
-// Built by tests/emu/Makefile into tests/emu/libgrsr_emu.so; loaded only by tests/.
+// emu_lib.cpp -- TEST INFRASTRUCTURE ONLY: runs the kernels of grsr_core.cuh / grsr_scenario.cuh on
+// the CPU through the fiber SIMT emulator (cuda_emu.hpp) so kernel logic can be checked where no GPU
+// exists.  Built by tests/emu/Makefile into tests/emu/libgrsr_emu.so; loaded only by tests/.
 #define GRSR_EMU 1
 #include "cuda_emu.hpp"
 #include "../../grsr_b200/csrc/grsr_core.cuh"
@@ -13,10 +13,12 @@ extern "C" int emu_dist_pairs(const int32_t *genomes, int G, int n, const int32_
   long long total = (long long)G * n;
   int32_t *sp = sinv.data();
   emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
-  size_t smem = grsr::work_bytes(n, false);
-  emu::launch((unsigned)grid, (unsigned)threads, smem, [&] {
-    grsr::dist_pairs_kernel(genomes, sp, n, pairs, npairs, out, stride);
-  });
+  int t, e;
+  grsr::pick_shape(n, threads, &t, &e);
+  size_t smem = grsr::work_bytes(n, t * e, false) + grsr::stage_bytes(n);
+  GRSR_DISPATCH_EPT(e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+    grsr::dist_pairs_kernel<kEpt>(genomes, sp, n, pairs, npairs, out, stride);
+  }));
   return 0;
 }
 
@@ -24,9 +26,11 @@ extern "C" int emu_scenario(const int32_t *src, const int32_t *dst, int npairs, 
                             int32_t *nsteps, int max_steps, int32_t *status,
                             unsigned long long *evals, int threads, int grid) {
   unsigned int ticket = 0;
-  size_t smem = grsr::work_bytes(n, true) + grsr::scen_extra_bytes(n);
-  emu::launch((unsigned)grid, (unsigned)threads, smem, [&] {
-    grsr::scenario_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket);
-  });
+  int t, e;
+  grsr::pick_shape(n, threads, &t, &e);
+  size_t smem = grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n);
+  GRSR_DISPATCH_EPT(e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+    grsr::scenario_kernel<kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket);
+  }));
   return 0;
 }
