@@ -267,7 +267,7 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
   Launch L;
   grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
   L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
-  GRSR_DISPATCH_EPT(L.ept, rc = finish_plan(grsr::scenario_kernel<kEpt>, npairs, L));
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
   if (rc) return rc;
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -285,7 +285,7 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
     CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(dtick.p, 0, 4, st));
-    GRSR_DISPATCH_EPT(L.ept, (grsr::scenario_kernel<kEpt><<<L.grid, L.threads, L.smem, st>>>(
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
         (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
         (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
     CK(cudaGetLastError());
@@ -379,9 +379,9 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   Launch L;
   grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
   L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
-  GRSR_DISPATCH_EPT(L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kEpt>, npairs, L));
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
   if (rc) return rc;
-  GRSR_DISPATCH_EPT(L.ept, (grsr::dist_pairs_kernel<kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
       d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
   CK(cudaGetLastError());
   return GRSR_OK;

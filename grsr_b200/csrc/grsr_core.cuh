@@ -38,13 +38,15 @@ static const unsigned kFull = 0xFFFFFFFFu;
 static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex within 227 KB smem
 
 // Jumping word of vertex v:  [31:17] label = smallest vertex seen on v's sigma-orbit window,
-//                            [16]    1 if an oriented grey edge was seen on that window,
-//                            [15]    1 if v is an end of an adjacency (then sigma(v) = v),
-//                            [14:0]  next = end of the window (sigma^k(v)).
+//                            [16:2]  next = end of the window (sigma^k(v)), i.e. bits [16:0] & ~3
+//                                    are the byte offset of W[next],
+//                            [1]     1 if an oriented grey edge was seen on that window,
+//                            [0]     1 if v is an end of an adjacency (then sigma(v) = v).
 #define GRSR_W_LABEL(w) ((w) >> 17)
-#define GRSR_W_NEXT(w) ((w) & 0x7FFFu)
-#define GRSR_W_ORBIT 0x10000u
-#define GRSR_W_ADJ 0x8000u
+#define GRSR_W_NEXT(w) (((w) >> 2) & 0x7FFFu)
+#define GRSR_W_ORBIT 2u
+#define GRSR_W_ADJ 1u
+#define GRSR_W_MAKE(label, next, flags) (((unsigned)(label) << 17) | ((unsigned)(next) << 2) | (flags))
 
 struct Stats { int d, b, c, h, f; };
 
@@ -162,7 +164,7 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
 // --------------------------------------------------------------------------------------------------
 // Hurdles and fortress for a graph that has at least one unoriented cycle.
 // Entry state: A2[v] = cycle id (leftmost vertex) or kNone for adjacency vertices;
-//              W[v] = converged jumping word of v (bit 16 = v's cycle owns an oriented grey edge).
+//              W[v] = converged jumping word of v (bit 1 = v's cycle owns an oriented grey edge).
 //              A1 is free.
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
@@ -176,7 +178,7 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
   //     reach (W[r+1] = rightmost vertex of cycle r, filled by S2).
   for (int k = tid; k <= n; k += nt) {
     unsigned a = 2u * k;
-    if (A2[a] == a) { A1[a] = (vid_t)((W[a] >> 16) & 1u); W[a] = a; W[a + 1] = 0; }
+    if (A2[a] == a) { A1[a] = (vid_t)((W[a] >> 1) & 1u); W[a] = a; W[a + 1] = 0; }
   }
   __syncthreads();
 
@@ -367,66 +369,80 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
 // gamma's gene t (vertex 2n+1 for t = n) -- which is what perm / invperm / greyEdges of the
 // reference encode (G/graph_edit.c:69-145, G/mcrdist.c:116-145).
 //
-// EPT = jumping words kept in registers per thread; blockDim.x * EPT == wk.Sp.
+// ends(t, L, R), t in [0, n): the vertices of the left and right end of gamma's t-th gene.
+// NT = threads per block, EPT = jumping words kept in registers per thread; NT * EPT == wk.Sp.
 // kKeepOrbits additionally leaves in wk.ORB[v] the sigma-orbit label of every vertex
 // (sigma(v) = grey[v^1]; kNone for the two ends of an adjacency); two breakpoint vertices x, y have
 // an even graphdist (G/graph_edit.c:1165-1238) exactly when ORB[x] == ORB[y].
 // All threads of the block must call; all receive the result.
 // --------------------------------------------------------------------------------------------------
-template <int EPT, bool kKeepOrbits, class InvFn>
-__device__ inline Stats dist_core(Work &wk, int n, InvFn inv) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+template <int NT, int EPT, bool kKeepOrbits, class EndsFn>
+__device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int S = wk.S;
   uint32_t *W = wk.W;
 
-  // phase A: one lane per grey edge t.  x = right end of gene t-1, y = left end of gene t.
-  // sigma(x^1) = y and sigma(y^1) = x seed the jumping words; the edge is an adjacency when x and
-  // y are the two ends of one black edge (G/mcrdist.c:135-140) and oriented when x and y have the
-  // same parity (G/graph_components.c:324-329).
+  // phase A: one lane per grey edge t = 0..n; each warp owns a contiguous run of edges so that the
+  // right end of gene t-1 arrives by shuffle.  x = right end of gene t-1 (vertex 0 for t = 0),
+  // y = left end of gene t (vertex 2n+1 for t = n).  sigma(x^1) = y and sigma(y^1) = x seed the
+  // jumping words; the edge is an adjacency when x and y are the two ends of one black edge
+  // (G/mcrdist.c:135-140) and oriented when x and y have the same parity
+  // (G/graph_components.c:324-329).
   unsigned nadj = 0;
-  for (int base = tid & ~31; base <= n; base += nt) {
-    int t = base + lane;
-    int q = (t < n) ? inv(t) : 0;
-    int qp = __shfl_up_sync(kFull, q, 1);
-    if (lane == 0 && t > 0 && t <= n) qp = inv(t - 1);
-    if (t <= n) {
-      unsigned x, y;
-      if (t == 0) x = 0;
-      else { unsigned p = (unsigned)(qp > 0 ? qp : -qp) - 1u; x = (qp > 0) ? 2u * p + 2u : 2u * p + 1u; }
-      if (t == n) y = (unsigned)S - 1u;
-      else { unsigned p = (unsigned)(q > 0 ? q : -q) - 1u; y = (q > 0) ? 2u * p + 1u : 2u * p + 2u; }
-      unsigned ob = (((x ^ y) & 1u) == 0u) ? GRSR_W_ORBIT : 0u;
-      unsigned xb = x ^ 1u, yb = y ^ 1u;
-      unsigned ab = (xb == y) ? GRSR_W_ADJ : 0u;
-      nadj += (xb == y);
-      W[xb] = (xb << 17) | ob | ab | y;
-      W[yb] = (yb << 17) | ob | ab | x;
+  {
+    const int per = ((((n + 1) + (NT >> 5) - 1) / (NT >> 5)) + 31) & ~31;
+    const int t0 = wid * per;
+    const int t1 = min(n + 1, t0 + per);
+    unsigned carry = 0;
+    if (t0 > 0 && t0 <= n) { unsigned l; ends(t0 - 1, l, carry); }
+    for (int base = t0; base < t1; base += 32) {
+      const int t = base + lane;
+      unsigned y = (unsigned)S - 1u, r = 0;
+      if (t < n) ends(t, y, r);
+      unsigned x = __shfl_up_sync(kFull, r, 1);
+      if (lane == 0) x = carry;
+      carry = __shfl_sync(kFull, r, 31);
+      if (t <= n) {
+        const unsigned xb = x ^ 1u, yb = y ^ 1u;
+        const unsigned fl = ((((x ^ y) & 1u) == 0u) ? GRSR_W_ORBIT : 0u) | ((xb == y) ? GRSR_W_ADJ : 0u);
+        nadj += (xb == y);
+        W[xb] = GRSR_W_MAKE(xb, y, fl);
+        W[yb] = GRSR_W_MAKE(yb, x, fl);
+      }
     }
   }
-  for (int v = S + tid; v < wk.Sp; v += nt) W[v] = ((unsigned)v << 17) | (unsigned)v;  // padding: self-loops
+  for (int v = S + tid; v < NT * EPT; v += NT) W[v] = GRSR_W_MAKE(v, v, GRSR_W_ADJ);  // padding
   __syncthreads();
 
   // phase B: pointer jumping along sigma with min-label and or-flag, in place.  Each word is one
-  // atomic 32-bit (label, flag, next) snapshot, so after round r every word covers >= 2^r
-  // successors; stop after ceil(log2(n+1)) rounds or as soon as a whole round changed nothing in
-  // the upper halves.  A thread keeps its EPT words in registers and only reads its successors.
+  // atomic 32-bit (label, next, flags) snapshot, so after round r every word covers >= 2^r
+  // successors; stop after ceil(log2(n+1)) rounds or as soon as a whole round changed no label and
+  // no flag.  A thread keeps its EPT words in registers; per round it gathers the words of its
+  // successors (in batches, loads before stores), merges and publishes.
   {
+    constexpr int UB = (EPT < 8) ? EPT : 8;
     uint32_t R[EPT];
 #pragma unroll
-    for (int j = 0; j < EPT; j++) R[j] = W[tid + j * nt];
+    for (int j = 0; j < EPT; j++) R[j] = W[tid + j * NT];
     const int rounds = ceil_log2(n + 1);
+    const char *Wb = (const char *)W;
     for (int r = 0; r < rounds; r++) {
       uint32_t chg = 0;
 #pragma unroll
-      for (int j = 0; j < EPT; j++) {
-        uint32_t w = R[j];
-        uint32_t wu = W[GRSR_W_NEXT(w)];
-        uint32_t nw = (min(w >> 17, wu >> 17) << 17) | ((w | wu) & GRSR_W_ORBIT) | (wu & 0xFFFFu);
-        chg |= (nw ^ w);
-        W[tid + j * nt] = nw;
-        R[j] = nw;
+      for (int j0 = 0; j0 < EPT; j0 += UB) {
+        uint32_t U[UB];
+#pragma unroll
+        for (int j = 0; j < UB; j++) U[j] = *(const uint32_t *)(Wb + (R[j0 + j] & 0x1FFFCu));
+#pragma unroll
+        for (int j = 0; j < UB; j++) {
+          const uint32_t w = R[j0 + j], wu = U[j];
+          const uint32_t nw = (min(w, wu) & 0xFFFE0000u) | (wu & 0x1FFFFu) | (w & GRSR_W_ORBIT);
+          chg |= (nw ^ w);
+          R[j0 + j] = nw;
+          W[tid + (j0 + j) * NT] = nw;
+        }
       }
-      if (!__syncthreads_or((chg >> 16) != 0)) break;
+      if (!__syncthreads_or((chg & 0xFFFE0002u) != 0)) break;
     }
   }
   __syncthreads();
@@ -435,15 +451,15 @@ __device__ inline Stats dist_core(Work &wk, int n, InvFn inv) {
   // orbit labels; the edge whose left end is its own cycle id is the cycle's root -> count cycles
   // and the roots whose orbit saw no oriented grey edge.
   unsigned ncyc = 0, nun = 0;
-  for (int k = tid; k <= n; k += nt) {
-    unsigned a = 2u * k;
-    uint32_t w0 = W[a], w1 = W[a + 1];
-    const bool adj = (w0 & GRSR_W_ADJ) != 0;
-    unsigned la = w0 >> 17, lb = w1 >> 17;
+  for (int k = tid; k <= n; k += NT) {
+    const unsigned a = 2u * k;
+    const uint2 ww = *(const uint2 *)(W + a);
+    const bool adj = (ww.x & GRSR_W_ADJ) != 0;
+    const unsigned la = ww.x >> 17, lb = ww.y >> 17;
     if (kKeepOrbits) ((uint32_t *)wk.ORB)[k] = adj ? 0xFFFFFFFFu : (la | (lb << 16));
     const bool root = !adj && (min(la, lb) == a);
     ncyc += root;
-    nun += (root && !(w0 & GRSR_W_ORBIT));
+    nun += (root && !(ww.x & GRSR_W_ORBIT));
   }
   unsigned long long tot =
       blk_sum_u64(((unsigned long long)nadj << 42) | ((unsigned long long)ncyc << 21) | nun, wk.red);
@@ -454,10 +470,10 @@ __device__ inline Stats dist_core(Work &wk, int n, InvFn inv) {
   if ((tot & 0x1FFFFFu) != 0) {
     // some cycle is unoriented: the component analysis is needed.  Cycle ids per vertex first.
     uint32_t *A2w = (uint32_t *)wk.A2;
-    for (int k = tid; k <= n; k += nt) {
-      unsigned a = 2u * k;
-      uint32_t w0 = W[a], w1 = W[a + 1];
-      unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(w0 >> 17, w1 >> 17);
+    for (int k = tid; k <= n; k += NT) {
+      const unsigned a = 2u * k;
+      const uint32_t w0 = W[a], w1 = W[a + 1];
+      const unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(w0 >> 17, w1 >> 17);
       A2w[k] = cy | (cy << 16);
     }
     __syncthreads();
@@ -468,14 +484,25 @@ __device__ inline Stats dist_core(Work &wk, int n, InvFn inv) {
   return st;
 }
 
-// inv for a pair of rows of the genome table: gamma in global memory, the signed inverse of pi
-// staged in shared memory (sinv[|g|-1] = +-(position+1) of gene |g| in pi).
-struct InvFromRows {
-  const int32_t *gamma; const int16_t *sinv_pi;
-  __device__ inline int operator()(int t) const {
-    int g = gamma[t];
-    int s = sinv_pi[(g > 0 ? g : -g) - 1];
-    return g > 0 ? s : -s;
+// Ends of a gene given its signed position q = +-(p+1) in pi: a forward gene at position p owns
+// vertices 2p+1 (left) and 2p+2 (right); a backward one has them swapped.
+__device__ inline void ends_from_signed_pos(int q, unsigned &L, unsigned &R) {
+  const unsigned a = (unsigned)(q > 0 ? q : -q), neg = (q < 0) ? 1u : 0u;
+  L = 2u * a - 1u + neg;
+  R = 2u * a - neg;
+}
+
+// ends() for a pair of rows of the genome table: gamma streamed from global memory, pi staged in
+// shared memory as tail[a-1] = the vertex where gene +a begins in pi (2p+1 if pi holds +a at
+// position p, 2p+2 if it holds -a); the other end of the gene is the other vertex of {2p+1, 2p+2}.
+struct EndsFromRows {
+  const int32_t *gamma; const uint16_t *tail;
+  __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
+    const int g = gamma[t];
+    const unsigned v = tail[(g > 0 ? g : -g) - 1];
+    const unsigned h = ((v - 1u) ^ 1u) + 1u;
+    L = (g > 0) ? v : h;
+    R = (g > 0) ? h : v;
   }
 };
 
@@ -495,43 +522,62 @@ __global__ void signed_inverse_kernel(const int32_t *__restrict__ genomes, int32
 
 __host__ __device__ inline size_t stage_bytes(int n) { return (((size_t)n * 2) + 15) & ~(size_t)15; }
 
-// Launch shape of the one-pair-per-block kernels: threads per block and jumping words per thread
-// (EPT, a power of two <= 64) with threads * EPT >= 2n+2.  About 16 words per thread keeps the
-// per-round loop in registers while several blocks stay resident per SM.
+// Launch shape of the one-pair-per-block kernels: threads per block (NT) and jumping words per
+// thread (EPT) with NT * EPT >= 2n+2, both compile-time in the kernels.  About 16 words per thread
+// keeps the per-round loop in registers while several blocks stay resident per SM.  Only the
+// combinations listed in GRSR_DISPATCH_SHAPE exist.
+__host__ inline bool shape_exists(int t, int e) {
+  if (t == 32) return e == 1 || e == 2 || e == 4 || e == 8 || e == 16;
+  if (t == 64) return e == 16;
+  if (t == 128 || t == 256) return e == 8 || e == 16 || e == 32;
+  if (t == 512) return e == 8 || e == 16 || e == 32 || e == 64;
+  return false;
+}
+
 __host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ept) {
-  int S = 2 * n + 2, t = 32;
-  if (forced_threads >= 32 && forced_threads <= 512 && (forced_threads % 32) == 0) t = forced_threads;
-  else while (t < 512 && t * 16 < S) t *= 2;
-  int e = 1;
+  const int S = 2 * n + 2;
+  int t = 32, e = 1;
+  while (t < 512 && t * 16 < S) t *= 2;
   while (e < 64 && t * e < S) e *= 2;
+  if (forced_threads > 0) {
+    int fe = 1;
+    while (fe < 64 && forced_threads * fe < S) fe *= 2;
+    if (shape_exists(forced_threads, fe) && forced_threads * fe >= S) { t = forced_threads; e = fe; }
+  }
   *threads = t; *ept = e;
 }
 
-#define GRSR_DISPATCH_EPT(ept, ...)                      \
-  switch (ept) {                                         \
-    case 1:  { constexpr int kEpt = 1;  __VA_ARGS__; } break; \
-    case 2:  { constexpr int kEpt = 2;  __VA_ARGS__; } break; \
-    case 4:  { constexpr int kEpt = 4;  __VA_ARGS__; } break; \
-    case 8:  { constexpr int kEpt = 8;  __VA_ARGS__; } break; \
-    case 16: { constexpr int kEpt = 16; __VA_ARGS__; } break; \
-    case 32: { constexpr int kEpt = 32; __VA_ARGS__; } break; \
-    default: { constexpr int kEpt = 64; __VA_ARGS__; } break; \
-  }
+#define GRSR_SHAPE_CASE(T, E, ...) \
+  if (nt_ == T && ept_ == E) { constexpr int kNt = T; constexpr int kEpt = E; __VA_ARGS__; } else
+#define GRSR_DISPATCH_SHAPE(threads, ept, ...)                                        \
+  do {                                                                                \
+    const int nt_ = (threads), ept_ = (ept);                                          \
+    GRSR_SHAPE_CASE(32, 1, __VA_ARGS__) GRSR_SHAPE_CASE(32, 2, __VA_ARGS__)           \
+    GRSR_SHAPE_CASE(32, 4, __VA_ARGS__) GRSR_SHAPE_CASE(32, 8, __VA_ARGS__)           \
+    GRSR_SHAPE_CASE(32, 16, __VA_ARGS__) GRSR_SHAPE_CASE(64, 16, __VA_ARGS__)         \
+    GRSR_SHAPE_CASE(128, 8, __VA_ARGS__) GRSR_SHAPE_CASE(128, 16, __VA_ARGS__)        \
+    GRSR_SHAPE_CASE(128, 32, __VA_ARGS__) GRSR_SHAPE_CASE(256, 8, __VA_ARGS__)        \
+    GRSR_SHAPE_CASE(256, 16, __VA_ARGS__) GRSR_SHAPE_CASE(256, 32, __VA_ARGS__)       \
+    GRSR_SHAPE_CASE(512, 8, __VA_ARGS__) GRSR_SHAPE_CASE(512, 16, __VA_ARGS__)        \
+    GRSR_SHAPE_CASE(512, 32, __VA_ARGS__) GRSR_SHAPE_CASE(512, 64, __VA_ARGS__) {}    \
+  } while (0)
+
+// registers per thread are capped so that the shared-memory-limited number of blocks fits
+#define GRSR_MIN_BLOCKS(NT, EPT) ((EPT) > 16 ? 1 : ((NT) >= 512 ? 3 : ((NT) == 256 ? 6 : ((NT) == 128 ? 10 : 16))))
 
 // Batched distance: pair p = (gamma row pairs[2p], pi row pairs[2p+1]) as in setinvmatrix
 // (reference G/uniinvdist.c:80-90).  stride 1: out[p] = d; stride 5: out[5p..] = {d,b,c,h,f}.
-// Block b owns the contiguous pairs [b*chunk, (b+1)*chunk); the signed inverse of pi stays staged in
-// shared memory while consecutive pairs share their pi row.
-template <int EPT>
-__global__ void __launch_bounds__(512, (EPT <= 16) ? 3 : 1)
+// Block b owns the contiguous pairs [b*chunk, (b+1)*chunk); pi stays staged in shared memory while
+// consecutive pairs share their pi row.
+template <int NT, int EPT>
+__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
 dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                   const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                   int stride) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
-  const int slots = blockDim.x * EPT;
-  work_carve(wk, smem_raw, n, slots, false);
-  int16_t *stage = (int16_t *)(smem_raw + work_bytes(n, slots, false));
+  work_carve(wk, smem_raw, n, NT * EPT, false);
+  uint16_t *stage = (uint16_t *)(smem_raw + work_bytes(n, NT * EPT, false));
   const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
   const long long p0 = (long long)blockIdx.x * chunk;
   const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
@@ -540,12 +586,15 @@ dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict
     const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
     if (pj != staged) {
       const int32_t *sp = sinv + (long long)pj * n;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) stage[i] = (int16_t)sp[i];
+      for (int i = threadIdx.x; i < n; i += NT) {
+        const int s = sp[i];
+        stage[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
+      }
       staged = pj;
       __syncthreads();
     }
-    InvFromRows inv; inv.gamma = genomes + (long long)gi * n; inv.sinv_pi = stage;
-    Stats st = dist_core<EPT, false>(wk, n, inv);
+    EndsFromRows ends; ends.gamma = genomes + (long long)gi * n; ends.tail = stage;
+    Stats st = dist_core<NT, EPT, false>(wk, n, ends);
     if (threadIdx.x == 0) {
       if (stride == 1) out[p] = st.d;
       else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }

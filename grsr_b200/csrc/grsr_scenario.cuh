@@ -55,20 +55,23 @@ struct RhoCurrent {
   }
 };
 
-// inv of G0 = graph(gamma = destination, pi = current) (G/opt_scenario.c:229): signed position in
-// the current genome of the destination's t-th gene = the inverse of rho0.
-struct InvG0 {
+// ends() of G0 = graph(gamma = destination, pi = current) (G/opt_scenario.c:229): the signed
+// position in the current genome of the destination's t-th gene is the inverse of rho0.
+struct EndsG0 {
   const int16_t *inv0;
-  __device__ inline int operator()(int t) const { return inv0[t]; }
+  __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
+    ends_from_signed_pos(inv0[t], L, R);
+  }
 };
 
-// inv of the trial evaluation invdist_noncircular(trial, dest) (G/opt_scenario.c:980), gamma =
+// ends() of the trial evaluation invdist_noncircular(trial, dest) (G/opt_scenario.c:980), gamma =
 // trial = current with [i..j] reversed and negated (G/scenario.c:475-486), pi = destination:
 // signed position in the destination of trial's t-th gene.
-struct InvTrial {
+struct EndsTrial {
   const int16_t *rho0; int i, j;
-  __device__ inline int operator()(int t) const {
-    return (t >= i && t <= j) ? -(int)rho0[i + j - t] : (int)rho0[t];
+  __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
+    const int q = (t >= i && t <= j) ? -(int)rho0[i + j - t] : (int)rho0[t];
+    ends_from_signed_pos(q, L, R);
   }
 };
 
@@ -78,24 +81,23 @@ struct InvTrial {
 
 // steps: npairs x max_steps (start, end) pairs; nsteps/status: per pair; evals: per pair number of
 // full trial evaluations (diagnostic, may be null); ticket: zero-initialised work counter.
-template <int EPT>
-__global__ void __launch_bounds__(512, (EPT <= 16) ? 3 : 1)
+template <int NT, int EPT>
+__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
 scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                 int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                 int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
                 unsigned int *ticket) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
-  const int slots = blockDim.x * EPT;
-  work_carve(wk, smem_raw, n, slots, true);
-  unsigned char *extra = smem_raw + work_bytes(n, slots, true);
+  work_carve(wk, smem_raw, n, NT * EPT, true);
+  unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, true);
   int16_t *CUR = (int16_t *)extra;
   int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
   int16_t *INV0 = (int16_t *)(extra + 2 * scen_arr_bytes(n));
   int16_t *RHO0 = (int16_t *)(extra + 3 * scen_arr_bytes(n));
   vid_t *BPL = (vid_t *)(extra + 4 * scen_arr_bytes(n));
   const vid_t *ORB = wk.ORB;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = NT;
   __shared__ int s_pair;
 
   for (;;) {
@@ -124,8 +126,8 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
         INV0[(r > 0 ? r : -r) - 1] = (int16_t)(r > 0 ? (i + 1) : -(i + 1));
       }
       __syncthreads();
-      InvG0 ig; ig.inv0 = INV0;
-      const Stats g0 = dist_core<EPT, true>(wk, n, ig);       // G/opt_scenario.c:229
+      EndsG0 eg; eg.inv0 = INV0;
+      const Stats g0 = dist_core<NT, EPT, true>(wk, n, eg);   // G/opt_scenario.c:229
       if (g0.d == 0) break;
       if (ns >= max_steps) { code = GRSR_SCEN_OVERFLOW; break; }
 
@@ -165,8 +167,8 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
         if (best == kNoKey) break;
         const int i = (int)(best & ((1u << kKeyShift) - 1u));
         const int j = i + (int)(best >> kKeyShift);
-        InvTrial it; it.rho0 = RHO0; it.i = i; it.j = j;
-        const Stats t1 = dist_core<EPT, false>(wk, n, it);    // G/opt_scenario.c:974-986
+        EndsTrial et; et.rho0 = RHO0; et.i = i; et.j = j;
+        const Stats t1 = dist_core<NT, EPT, false>(wk, n, et);  // G/opt_scenario.c:974-986
         nevals++;
         if (t1.d == g0.d - 1) { fi = i; fj = j; break; }
         lastkey = best;

@@ -16,8 +16,8 @@ extern "C" int emu_dist_pairs(const int32_t *genomes, int G, int n, const int32_
   int t, e;
   grsr::pick_shape(n, threads, &t, &e);
   size_t smem = grsr::work_bytes(n, t * e, false) + grsr::stage_bytes(n);
-  GRSR_DISPATCH_EPT(e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
-    grsr::dist_pairs_kernel<kEpt>(genomes, sp, n, pairs, npairs, out, stride);
+  GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+    grsr::dist_pairs_kernel<kNt, kEpt>(genomes, sp, n, pairs, npairs, out, stride);
   }));
   return 0;
 }
@@ -29,8 +29,8 @@ extern "C" int emu_scenario(const int32_t *src, const int32_t *dst, int npairs, 
   int t, e;
   grsr::pick_shape(n, threads, &t, &e);
   size_t smem = grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n);
-  GRSR_DISPATCH_EPT(e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
-    grsr::scenario_kernel<kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket);
+  GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+    grsr::scenario_kernel<kNt, kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket);
   }));
   return 0;
 }
