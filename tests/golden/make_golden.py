@@ -102,6 +102,23 @@ CLI_CASES = [
 ]
 
 
+def fortress_genomes(n=63):
+    """identity + fortress-heavy rows (f = 1 against the identity for several of them)."""
+    ident = list(range(1, n + 1))
+    rows = [ident]
+    for units in (3, 5, 7, 9):
+        p = gen.fortress_chain(units)
+        rows.append(p + list(range(len(p) + 1, n + 1)))
+    seed = 0
+    while len(rows) < 16:
+        p = gen.hurdle_rich_perm(n, 5000 + seed)
+        seed += 1
+        st = U.orc_stats(np.array([ident, p], dtype=np.int32), [[0, 1]])[0]
+        if st[4] == 1:
+            rows.append(p)
+    return np.asarray(rows, dtype=np.int32)
+
+
 def run_ref(args, cwd):
     r = subprocess.run([GRIMM] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     return r.returncode, r.stdout.decode(), r.stderr.decode()
@@ -194,6 +211,10 @@ def main():
         pairs = np.array([[i, j] for i in range(len(g)) for j in range(len(g))], dtype=np.int32)
         blobs["g%d" % n] = g
         blobs["s%d" % n] = U.ref_stats(g, pairs)
+    g = fortress_genomes()
+    pairs = np.array([[i, j] for i in range(len(g)) for j in range(len(g))], dtype=np.int32)
+    blobs["gfort"] = g
+    blobs["sfort"] = U.ref_stats(g, pairs)
     np.savez_compressed(os.path.join(HERE, "stats_mixed.npz"), **blobs)
 
     scen = []

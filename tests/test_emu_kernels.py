@@ -1,0 +1,66 @@
+"""The kernel SOURCE (grsr_core.cuh / grsr_scenario.cuh) executed on the CPU by the SIMT emulator
+(tests/emu) and compared with the oracle.  This does not replace the GPU parity tests -- it lets the
+kernel logic (indexing, barriers, warp collectives, every block shape) be checked where no GPU
+exists.  Sizes are small because each emulated thread is a fiber."""
+import random
+
+import numpy as np
+import pytest
+
+import _util as U
+from grsr_b200 import gen
+
+
+def _ordered(G):
+    return np.array([[i, j] for i in range(G) for j in range(G)], dtype=np.int32)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_emulated_distance_exhaustive(n):
+    perms = U.all_signed_perms(n)
+    g = np.vstack([np.arange(1, n + 1, dtype=np.int32)[None, :], perms])
+    k = len(g)
+    pairs = np.array([[0, i] for i in range(1, k)] + [[i, 0] for i in range(1, k)], dtype=np.int32)
+    assert np.array_equal(U.emu_stats(g, pairs, 0, 3), U.orc_stats(g, pairs))
+
+
+# (n, forced threads): 0 = the shape pick_shape chooses; the others force other kernel instances
+@pytest.mark.parametrize("n,threads", [(7, 0), (15, 0), (16, 0), (33, 0), (63, 0), (64, 0), (127, 0),
+                                        (255, 0), (300, 128), (300, 256), (600, 0), (1100, 0), (1100, 512)])
+def test_emulated_distance_structured(n, threads):
+    g = U.mixed_genomes(n, 12 if n < 200 else 6, seed=n)
+    pairs = _ordered(len(g))
+    got = U.emu_stats(g, pairs, threads, 3)
+    assert np.array_equal(got, U.orc_stats(g, pairs))
+
+
+def test_emulated_fortress_fixture():
+    z = np.load(U.GOLDEN + "/stats_mixed.npz")
+    g = z["gfort"]
+    assert np.array_equal(U.emu_stats(g, _ordered(len(g)), 0, 2), z["sfort"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 29, 40])
+def test_emulated_scenarios(n):
+    srcs, dsts = [], []
+    for s in range(8):
+        seed = n * 100 + s
+        rng = random.Random(seed)
+        kind = s % 4
+        if kind == 0:
+            src, dst = gen.random_signed_perm(n, rng), gen.random_signed_perm(n, rng)
+        elif kind == 1:
+            src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
+        elif kind == 2:
+            src, dst = list(range(1, n + 1)), gen.hurdle_rich_perm(n, seed)
+        else:
+            src = gen.k_reversal_perm(n, rng.randrange(1, 8), rng)
+            dst = gen.k_reversal_perm(n, rng.randrange(0, 5), rng)
+        srcs.append(src)
+        dsts.append(dst)
+    steps, status, evals = U.emu_scenario(srcs, dsts, 0, 3)
+    for q in range(len(srcs)):
+        want, want_evals = U.orc_scenario(srcs[q], dsts[q])
+        assert status[q] == 0
+        assert np.array_equal(steps[q], want)
+        assert evals[q] == want_evals      # same candidates tried in the same order
