@@ -49,7 +49,7 @@ def workload_config(extra=None):
         "workload": "config3: all-pairs reversal distance, 1000 genomes x 2000 signed blocks "
                     "(499500 pairs), synthetic seed 7, circular-aligned (-C -m)",
         "genomes": G_CFG, "genes": N_CFG, "pairs": G_CFG * (G_CFG - 1) // 2,
-        "sharding": "contiguous slices of the row-major upper triangle, one per rank, no collective",
+        "sharding": "contiguous slices of the column-by-column upper triangle, one per rank, no collective",
     }
     if extra:
         cfg.update(extra)
@@ -134,7 +134,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     genomes = make_genomes()
-    pairs = gen.all_pairs(G_CFG)
+    j, i = np.tril_indices(G_CFG, k=-1)
+    pairs = np.stack([i, j], axis=1).astype(np.int32)   # column-by-column triangle, as the GPU arm
     kind, run = load_cpu_reference()
     cores = os.cpu_count() or 1
     # size one step for a few seconds so that steps+warmup stay within minutes
@@ -326,7 +327,7 @@ def run_gpu_arm(args):
                     "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "pairs_per_launch": cnt, "peak_source": peak_src}
         cpu = None
         if world == 1 and not args.no_cpu:
-            pairs = gen.all_pairs(G_CFG)
+            pairs = capi.triangle_pairs(G_CFG)          # same flat order as the GPU result
             cpu, d_cpu, sample = cpu_sample_rate(genomes, pairs, seconds=12.0)
             if not np.array_equal(d_cpu, o_np[:len(sample)]):
                 raise SystemExit("GPU distances differ from the CPU reference on the baseline sample")
