@@ -32,6 +32,7 @@ SIGNATURES = {
     "grsr_last_error": (ctypes.c_char_p, []),
     "grsr_device_count": (ctypes.c_int, []),
     "grsr_max_genes": (ctypes.c_int, []),
+    "grsr_max_genes_on_chip": (ctypes.c_int, [ctypes.c_int]),
     "grsr_release": (None, []),
     "grsr_dist_pairs": (ctypes.c_int, [I32P, ctypes.c_int, ctypes.c_int, I32P, ctypes.c_int64, I32P,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]),
@@ -85,6 +86,10 @@ def device_count() -> int:
 
 def max_genes() -> int:
     return lib().grsr_max_genes()
+
+
+def max_genes_on_chip(scenario: bool = False) -> int:
+    return lib().grsr_max_genes_on_chip(1 if scenario else 0)
 
 
 def release() -> None:

@@ -57,6 +57,46 @@ int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    if (p) { cudaFree(p); p = nullptr; }
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return GRSR_OK;
+  }
+};
+
+// Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
+// survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
+// 20 MB around it would cost as much again).  One call at a time per device (mutex).
+const int kCacheSlots = 6;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4 large-build scratch
+struct DevCache {
+  std::recursive_mutex mu;
+  cudaStream_t stream = nullptr;
+  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0};
+};
+const int kMaxDevices = 64;
+DevCache g_cache[kMaxDevices];
+
+int cache_reserve(DevCache &c, int slot, size_t bytes, void **out) {
+  if (c.cap[slot] < bytes) {
+    if (c.buf[slot]) { cudaFree(c.buf[slot]); c.buf[slot] = nullptr; c.cap[slot] = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&c.buf[slot], want);
+    if (e != cudaSuccess)
+      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    c.cap[slot] = want;
+  }
+  *out = c.buf[slot];
+  return GRSR_OK;
+}
+
 struct Launch { int threads; int ept; int grid; size_t smem; };
 
 // Shape, shared memory and grid of a one-pair-per-block kernel instance `kernel` (already
@@ -87,13 +127,45 @@ int finish_plan(K kernel, long long units, Launch &L) {
   return GRSR_OK;
 }
 
-int check_genes_fit(int n, bool scenario) {
-  int lim = scenario ? grsr_max_genes() : grsr::kMaxSmemGenes;
-  if (n > lim)
-    return fail(GRSR_ERR_TOOLARGE,
-                "num_genes=%d: this build keeps the breakpoint graph in shared memory and accepts at "
-                "most %d genes for %s", n, lim, scenario ? "scenarios" : "distances");
+const int kMaxLargeGenes = 1000000;   // global-memory build: 31-bit ids, 21-bit packed counters
+
+// which build serves num_genes = n: the shared-memory one while the pair's graph fits on chip,
+// the global-memory one beyond (or when GRSR_FORCE_LARGE is set, for tests)
+bool small_fits(int n, bool scenario) {
+  if (env_int("GRSR_FORCE_LARGE", 0)) return false;
+  if (n > grsr::kMaxSmemGenes || 2 * n + 2 > 32767) return false;
+  int t, e;
+  grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &t, &e);
+  if (t * e < 2 * n + 2) return false;
+  size_t smem = scenario ? grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n)
+                         : grsr::work_bytes(n, t * e, false) + grsr::stage_bytes(n);
+  return smem <= 227u * 1024u;
+}
+
+int check_genes_fit(int n) {
+  if (n > kMaxLargeGenes)
+    return fail(GRSR_ERR_TOOLARGE, "num_genes=%d: this build accepts at most %d genes", n,
+                kMaxLargeGenes);
   return GRSR_OK;
+}
+
+// grid and per-block scratch of the large build: one 1024-thread block per resident slot
+template <class K>
+int plan_large(K kernel, long long units, size_t bytes_per_block, int dev, int *grid, void **scratch) {
+  DevInfo di;
+  int rc = dev_info(dev, di);
+  if (rc) return rc;
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 1024, 0));
+  if (occ < 1) return fail(GRSR_ERR_CUDA, "large kernel does not fit on an SM");
+  long long g = (long long)di.sms * occ;
+  if (g > units) g = units;
+  if (g < 1) g = 1;
+  *grid = (int)g;
+  if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
+  DevCache &c = g_cache[dev];
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  return cache_reserve(c, 4, bytes_per_block * (size_t)g, scratch);
 }
 
 // Upper triangle enumerated column by column -- (0,1), (0,2), (1,2), (0,3), ... -- so that
@@ -150,45 +222,6 @@ int check_genomes(const int32_t *genomes, long long rows, int n) {
   return GRSR_OK;
 }
 
-struct DevBuf {
-  void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) {
-    if (p) { cudaFree(p); p = nullptr; }
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    }
-    return GRSR_OK;
-  }
-};
-
-// Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
-// survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
-// 20 MB around it would cost as much again).  One call at a time per device (mutex).
-struct DevCache {
-  std::mutex mu;
-  cudaStream_t stream = nullptr;
-  void *buf[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t cap[4] = {0, 0, 0, 0};
-};
-const int kMaxDevices = 64;
-DevCache g_cache[kMaxDevices];
-
-int cache_reserve(DevCache &c, int slot, size_t bytes, void **out) {
-  if (c.cap[slot] < bytes) {
-    if (c.buf[slot]) { cudaFree(c.buf[slot]); c.buf[slot] = nullptr; c.cap[slot] = 0; }
-    size_t want = bytes + bytes / 4 + 256;
-    cudaError_t e = cudaMalloc(&c.buf[slot], want);
-    if (e != cudaSuccess)
-      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
-    c.cap[slot] = want;
-  }
-  *out = c.buf[slot];
-  return GRSR_OK;
-}
-
 enum PairSource { PAIRS_LIST, PAIRS_TRIANGLE, PAIRS_SQUARE };
 
 // One device's share of a pair job: copy the genome table in, build the signed inverses, obtain the
@@ -200,7 +233,7 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
   if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
   DevCache &c = g_cache[dev];
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
   if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   cudaStream_t st = c.stream;
   size_t gbytes = (size_t)G * n * sizeof(int32_t);
@@ -263,11 +296,18 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  if ((rc = check_genes_fit(n, true))) return rc;
+  if ((rc = check_genes_fit(n))) return rc;
+  const bool small = small_fits(n, true);
   Launch L;
-  grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
-  L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
-  GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
+  L.threads = 1024; L.ept = 0; L.smem = 0; L.grid = 1;
+  void *scratch = nullptr;
+  if (small) {
+    grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
+  } else {
+    rc = plan_large(grsr::scenario_large_kernel, npairs, grsr::scen_large_bytes(n), dev, &L.grid, &scratch);
+  }
   if (rc) return rc;
   cudaStream_t st;
   CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -285,9 +325,16 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
     CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(dtick.p, 0, 4, st));
-    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
-        (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
-        (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
+    if (small) {
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
+          (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
+          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
+    } else {
+      grsr::scenario_large_kernel<<<L.grid, 1024, 0, st>>>(
+          (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
+          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p,
+          (unsigned char *)scratch);
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(steps, dsteps.p, sbytes, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(nsteps, dns.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
@@ -326,25 +373,21 @@ int grsr_device_count(void) {
 void grsr_release(void) {
   for (int d = 0; d < kMaxDevices; d++) {
     DevCache &c = g_cache[d];
-    std::lock_guard<std::mutex> lk(c.mu);
+    std::lock_guard<std::recursive_mutex> lk(c.mu);
     bool any = c.stream != nullptr;
-    for (int k = 0; k < 4; k++) any = any || c.buf[k];
+    for (int k = 0; k < kCacheSlots; k++) any = any || c.buf[k];
     if (!any) continue;
     if (cudaSetDevice(d) != cudaSuccess) { cudaGetLastError(); continue; }
-    for (int k = 0; k < 4; k++) { if (c.buf[k]) cudaFree(c.buf[k]); c.buf[k] = nullptr; c.cap[k] = 0; }
+    for (int k = 0; k < kCacheSlots; k++) { if (c.buf[k]) cudaFree(c.buf[k]); c.buf[k] = nullptr; c.cap[k] = 0; }
     if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
   }
 }
 
-int grsr_max_genes(void) {
+int grsr_max_genes(void) { return kMaxLargeGenes; }
+
+int grsr_max_genes_on_chip(int scenario) {
   int n = grsr::kMaxSmemGenes;
-  for (; n > 1; n--) {
-    int t, e;
-    grsr::pick_shape(n, 0, &t, &e);
-    if (t * e >= 2 * n + 2 &&
-        grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n) <= 227u * 1024u)
-      break;
-  }
+  while (n > 1 && !small_fits(n, scenario != 0)) n--;
   return n;
 }
 
@@ -374,15 +417,26 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   if (npairs <= 0) return GRSR_OK;
   if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
   if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
-  int rc = check_genes_fit(num_genes, false);
+  int rc = check_genes_fit(num_genes);
   if (rc) return rc;
-  Launch L;
-  grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
-  L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
-  GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
-  if (rc) return rc;
-  GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
-      d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
+  if (small_fits(num_genes, false)) {
+    Launch L;
+    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
+    if (rc) return rc;
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
+  } else {
+    int dev, grid;
+    void *scratch = nullptr;
+    CK(cudaGetDevice(&dev));
+    rc = plan_large(grsr::dist_pairs_large_kernel, npairs, grsr::large_work_bytes(num_genes, false), dev,
+                    &grid, &scratch);
+    if (rc) return rc;
+    grsr::dist_pairs_large_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride, (unsigned char *)scratch);
+  }
   CK(cudaGetLastError());
   return GRSR_OK;
 }

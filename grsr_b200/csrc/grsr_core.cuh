@@ -33,7 +33,6 @@
 namespace grsr {
 
 typedef uint16_t vid_t;
-static const unsigned kNone = 0xFFFFu;
 static const unsigned kFull = 0xFFFFFFFFu;
 static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex within 227 KB smem
 
@@ -50,17 +49,24 @@ static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex 
 
 struct Stats { int d, b, c, h, f; };
 
-// Shared-memory workspace of one pair.  S = 2n+2 vertices, padded to Sp = a multiple of the
-// block's slots (threads x words per thread, see dist_core) so that no bounds checks are needed.
-struct Work {
-  uint32_t *W;              // [Sp] jumping words; later per-root scratch of the slow path
-  vid_t *A1;                // [S]  slow path: per-root flags/links, then compacted lists
-  vid_t *A2;                // [S]  slow path: cycle id per vertex, then compacted lists
-  vid_t *ORB;               // [S]  sigma-orbit label per vertex (scenario kernels only)
-  vid_t *BLK;               // [2*NB] per-32-vertex block: min cycle id, max cycle reach
-  unsigned long long *red;  // [34] reduction scratch
+template <class VT> __host__ __device__ constexpr unsigned none_of() { return (unsigned)(VT)(~(VT)0); }
+
+// Workspace of one pair.  S = 2n+2 vertices.  VT = vertex id type: uint16_t when the graph lives in
+// shared memory (2n+2 <= 32767), uint32_t for the global-memory build used beyond that.
+template <class VT>
+struct WorkT {
+  void *W;                  // jumping words: uint32_t[Sp] (shared-memory build, Sp = slots of the
+                            //   block) or uint64_t[S] (global-memory build)
+  uint32_t *P;              // [S] per-cycle scratch of the slow path (parent / reach / counters);
+                            //   aliases W in the shared-memory build
+  VT *A1;                   // [S]  slow path: per-root flags/links, then compacted lists
+  VT *A2;                   // [S]  slow path: cycle id per vertex, then compacted lists
+  VT *ORB;                  // [S]  sigma-orbit label per vertex (scenario kernels only)
+  VT *BLK;                  // [2*NB] per-32-vertex block: min cycle id, max cycle reach
+  unsigned long long *red;  // [34] reduction scratch (always shared memory)
   int S, Sp, NB;
 };
+typedef WorkT<uint16_t> Work;
 
 __host__ __device__ inline int padded_size(int n, int slots) {
   int s = 2 * n + 2;
@@ -80,7 +86,7 @@ __host__ __device__ inline size_t work_bytes(int n, int slots, bool keep_orbits)
 __device__ inline void work_carve(Work &wk, unsigned char *base, int n, int slots, bool keep_orbits) {
   int sp = padded_size(n, slots), sv = (2 * n + 2 + 7) & ~7;
   wk.S = 2 * n + 2; wk.Sp = sp; wk.NB = num_vblocks(n);
-  wk.W = (uint32_t *)base;  base += (size_t)sp * 4;
+  wk.W = (void *)base; wk.P = (uint32_t *)base;  base += (size_t)sp * 4;
   wk.A1 = (vid_t *)base;    base += (size_t)sv * 2;
   wk.A2 = (vid_t *)base;    base += (size_t)sv * 2;
   wk.ORB = keep_orbits ? (vid_t *)base : (vid_t *)0;
@@ -125,8 +131,8 @@ __device__ inline unsigned blk_max_u32(unsigned v, unsigned long long *red) {
 
 // Ordered compaction: out[0..total) = value(i) for the i in [0,N) with f(i, value) true, in
 // increasing i.  Each warp owns a contiguous chunk, counts with ballots, then writes.
-template <class F>
-__device__ inline int blk_compact(int N, F f, vid_t *out, unsigned long long *red) {
+template <class VT, class F>
+__device__ inline int blk_compact(int N, F f, VT *out, unsigned long long *red) {
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int chunk = (((N + nw - 1) / nw) + 31) & ~31;
   int lo = wid * chunk, hi = min(N, lo + chunk);
@@ -145,7 +151,7 @@ __device__ inline int blk_compact(int N, F f, vid_t *out, unsigned long long *re
     int i = base + lane; unsigned val = 0;
     bool ok = (i < hi) && f(i, val);
     unsigned m = __ballot_sync(kFull, ok);
-    if (ok) out[pos + __popc(m & ((1u << lane) - 1u))] = (vid_t)val;
+    if (ok) out[pos + __popc(m & ((1u << lane) - 1u))] = (VT)val;
     pos += __popc(m);
   }
   __syncthreads();
@@ -163,22 +169,25 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
 
 // --------------------------------------------------------------------------------------------------
 // Hurdles and fortress for a graph that has at least one unoriented cycle.
-// Entry state: A2[v] = cycle id (leftmost vertex) or kNone for adjacency vertices;
-//              W[v] = converged jumping word of v (bit 1 = v's cycle owns an oriented grey edge).
-//              A1 is free.
+// Entry state: A2[v] = cycle id (leftmost vertex) or NONE for adjacency vertices;
+//              A1[r] = 1 if cycle r (r = its leftmost vertex, always even) owns an oriented grey
+//              edge, else 0.  P is free (it may alias the jumping words, which are dead by now).
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
-__device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
+template <class VT>
+__device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int S = wk.S;
-  uint32_t *W = wk.W; vid_t *A1 = wk.A1, *A2 = wk.A2, *BLK = wk.BLK;
-  vid_t *bmin = BLK, *bmax = BLK + wk.NB;
+  constexpr unsigned kNone = none_of<VT>();
+  constexpr unsigned kNoLink = kNone & ~1u;
+  uint32_t *W = wk.P; VT *A1 = wk.A1, *A2 = wk.A2, *BLK = wk.BLK;
+  VT *bmin = BLK, *bmax = BLK + wk.NB;
 
-  // S1: park the orientation flag in A1[r], start the union-find forest (W[r] = r) and the
-  //     reach (W[r+1] = rightmost vertex of cycle r, filled by S2).
+  // S1: start the union-find forest (W[r] = r) and the reach (W[r+1] = rightmost vertex of
+  //     cycle r, filled by S2).
   for (int k = tid; k <= n; k += nt) {
     unsigned a = 2u * k;
-    if (A2[a] == a) { A1[a] = (vid_t)((W[a] >> 1) & 1u); W[a] = a; W[a + 1] = 0; }
+    if (A2[a] == a) { W[a] = a; W[a + 1] = 0; }
   }
   __syncthreads();
 
@@ -202,7 +211,7 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
         if (c != kNone) { mn = min(mn, c); mx = max(mx, W[c + 1]); }
       }
     }
-    bmin[B] = (vid_t)mn; bmax[B] = (vid_t)mx;
+    bmin[B] = (VT)mn; bmax[B] = (VT)mx;
   }
   __syncthreads();
 
@@ -241,10 +250,10 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
       mn = __reduce_min_sync(kFull, mn);
       mx = __reduce_max_sync(kFull, mx);
       if (lane == src) {
-        unsigned lk1 = (mn < rr) ? mn : 0xFFFEu;
+        unsigned lk1 = (mn < rr) ? mn : kNoLink;
         unsigned lk2 = (mx > RR) ? (unsigned)A2[mx] : kNone;
-        A1[rr] = (vid_t)((A1[rr] & 1u) | lk1);
-        A1[rr + 1] = (vid_t)lk2;
+        A1[rr] = (VT)((A1[rr] & 1u) | lk1);
+        A1[rr + 1] = (VT)lk2;
       }
     }
   }
@@ -258,8 +267,8 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
       unsigned r = 2u * k;
       if (A2[r] != r) continue;
       unsigned me = uf_find(W, r);
-      unsigned l1 = A1[r] & 0xFFFEu, l2 = A1[r + 1];
-      if (l1 != 0xFFFEu) {
+      unsigned l1 = A1[r] & kNoLink, l2 = A1[r + 1];
+      if (l1 != kNoLink) {
         unsigned o = uf_find(W, l1);
         if (o != me) { atomicMin(&W[max(o, me)], min(o, me)); changed = 1; }
       }
@@ -307,7 +316,7 @@ __device__ inline unsigned hurdles_slow_path(Work &wk, int n) {
     if (t > 0 && A1[t - 1] == c) return false;
     val = c; return true;
   }, A2, wk.red);
-  const vid_t *run = A2;
+  const VT *run = A2;
 
   // S9: per component: number of runs (W[c]) and 1 + index of its last run (W[c+1]).
   for (int t = tid; t < nb; t += nt) { unsigned c = run[t]; W[c] = 0; W[c + 1] = 0; }
@@ -380,7 +389,8 @@ template <int NT, int EPT, bool kKeepOrbits, class EndsFn>
 __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int S = wk.S;
-  uint32_t *W = wk.W;
+  constexpr unsigned kNone = none_of<uint16_t>();
+  uint32_t *W = (uint32_t *)wk.W;
 
   // phase A: one lane per grey edge t = 0..n; each warp owns a contiguous run of edges so that the
   // right end of gene t-1 arrives by shuffle.  x = right end of gene t-1 (vertex 0 for t = 0),
@@ -468,13 +478,15 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   st.c = (int)((tot >> 21) & 0x1FFFFFu);
   st.h = 0; st.f = 0;
   if ((tot & 0x1FFFFFu) != 0) {
-    // some cycle is unoriented: the component analysis is needed.  Cycle ids per vertex first.
+    // some cycle is unoriented: the component analysis is needed.  Cycle id per vertex and the
+    // orientation flag of every cycle first.
     uint32_t *A2w = (uint32_t *)wk.A2;
     for (int k = tid; k <= n; k += NT) {
       const unsigned a = 2u * k;
       const uint32_t w0 = W[a], w1 = W[a + 1];
       const unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(w0 >> 17, w1 >> 17);
       A2w[k] = cy | (cy << 16);
+      wk.A1[a] = (uint16_t)((w0 >> 1) & 1u);
     }
     __syncthreads();
     unsigned hf = hurdles_slow_path(wk, n);
@@ -482,6 +494,131 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   }
   st.d = st.b - st.c + st.h + st.f;
   return st;
+}
+
+// --------------------------------------------------------------------------------------------------
+// dist_core_large: the same pipeline for graphs that do not fit shared memory (2n+2 > 32767 or the
+// block's shared-memory budget): 32-bit vertex ids, 64-bit jumping words
+//   [63:33] label | [32:2] next | [1] oriented edge seen | [0] adjacency
+// in a global-memory (L2-resident) workspace, one block per pair, words re-read every round
+// instead of living in registers.  Phases and results are those of dist_core.
+// --------------------------------------------------------------------------------------------------
+#define GRSR_L_MAKE(label, next, flags) \
+  (((unsigned long long)(label) << 33) | ((unsigned long long)(next) << 2) | (unsigned long long)(flags))
+#define GRSR_L_NEXT(w) ((unsigned)(((w) >> 2) & 0x7FFFFFFFull))
+#define GRSR_L_LABEL(w) ((unsigned)((w) >> 33))
+
+template <bool kKeepOrbits, class EndsFn>
+__device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const int S = wk.S;
+  constexpr unsigned kNone = none_of<uint32_t>();
+  unsigned long long *W = (unsigned long long *)wk.W;
+
+  unsigned nadj = 0;
+  {
+    const int nwarps = nt >> 5;
+    const int per = ((((n + 1) + nwarps - 1) / nwarps) + 31) & ~31;
+    const int t0 = wid * per;
+    const int t1 = min(n + 1, t0 + per);
+    unsigned carry = 0;
+    if (t0 > 0 && t0 <= n) { unsigned l; ends(t0 - 1, l, carry); }
+    for (int base = t0; base < t1; base += 32) {
+      const int t = base + lane;
+      unsigned y = (unsigned)S - 1u, r = 0;
+      if (t < n) ends(t, y, r);
+      unsigned x = __shfl_up_sync(kFull, r, 1);
+      if (lane == 0) x = carry;
+      carry = __shfl_sync(kFull, r, 31);
+      if (t <= n) {
+        const unsigned xb = x ^ 1u, yb = y ^ 1u;
+        const unsigned fl = ((((x ^ y) & 1u) == 0u) ? GRSR_W_ORBIT : 0u) | ((xb == y) ? GRSR_W_ADJ : 0u);
+        nadj += (xb == y);
+        W[xb] = GRSR_L_MAKE(xb, y, fl);
+        W[yb] = GRSR_L_MAKE(yb, x, fl);
+      }
+    }
+  }
+  __syncthreads();
+
+  {
+    const int rounds = ceil_log2(n + 1);
+    for (int r = 0; r < rounds; r++) {
+      unsigned long long chg = 0;
+      for (int v0 = tid; v0 < S; v0 += 4 * nt) {
+        unsigned long long w[4], u[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { int v = v0 + j * nt; w[j] = (v < S) ? W[v] : 0ull; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) { int v = v0 + j * nt; u[j] = (v < S) ? W[GRSR_L_NEXT(w[j])] : 0ull; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int v = v0 + j * nt;
+          if (v < S) {
+            const unsigned long long m = (w[j] < u[j]) ? w[j] : u[j];
+            const unsigned long long nw = (m & 0xFFFFFFFE00000000ull) | (u[j] & 0x1FFFFFFFFull) | (w[j] & 2ull);
+            if (nw != w[j]) { W[v] = nw; chg |= (nw ^ w[j]); }
+          }
+        }
+      }
+      if (!__syncthreads_or((chg & 0xFFFFFFFE00000002ull) != 0ull)) break;
+    }
+  }
+  __syncthreads();
+
+  unsigned ncyc = 0, nun = 0;
+  for (int k = tid; k <= n; k += nt) {
+    const unsigned a = 2u * k;
+    const unsigned long long w0 = W[a], w1 = W[a + 1];
+    const bool adj = (w0 & GRSR_W_ADJ) != 0;
+    const unsigned la = GRSR_L_LABEL(w0), lb = GRSR_L_LABEL(w1);
+    if (kKeepOrbits) { wk.ORB[a] = adj ? kNone : la; wk.ORB[a + 1] = adj ? kNone : lb; }
+    const bool root = !adj && (min(la, lb) == a);
+    ncyc += root;
+    nun += (root && !(w0 & GRSR_W_ORBIT));
+  }
+  unsigned long long tot =
+      blk_sum_u64(((unsigned long long)nadj << 42) | ((unsigned long long)ncyc << 21) | nun, wk.red);
+  Stats st;
+  st.b = (n + 1) - (int)(tot >> 42);
+  st.c = (int)((tot >> 21) & 0x1FFFFFu);
+  st.h = 0; st.f = 0;
+  if ((tot & 0x1FFFFFu) != 0) {
+    for (int k = tid; k <= n; k += nt) {
+      const unsigned a = 2u * k;
+      const unsigned long long w0 = W[a], w1 = W[a + 1];
+      const unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(GRSR_L_LABEL(w0), GRSR_L_LABEL(w1));
+      wk.A2[a] = cy; wk.A2[a + 1] = cy;
+      wk.A1[a] = (unsigned)((w0 >> 1) & 1ull);
+    }
+    __syncthreads();
+    unsigned hf = hurdles_slow_path(wk, n);
+    st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
+  }
+  st.d = st.b - st.c + st.h + st.f;
+  return st;
+}
+
+// global-memory workspace of the large build, per block
+__host__ __device__ inline size_t large_work_bytes(int n, bool keep_orbits) {
+  size_t sv = (size_t)((2 * n + 2 + 7) & ~7);
+  size_t b = sv * 8 + sv * 4 /*P*/ + sv * 4 + sv * 4 + (keep_orbits ? sv * 4 : 0);
+  b += (((size_t)num_vblocks(n) * 2 * 4) + 15) & ~(size_t)15;
+  return (b + 255) & ~(size_t)255;
+}
+
+__device__ inline void large_work_carve(WorkT<uint32_t> &wk, unsigned char *base, int n, bool keep_orbits,
+                                        unsigned long long *red_smem) {
+  size_t sv = (size_t)((2 * n + 2 + 7) & ~7);
+  wk.S = 2 * n + 2; wk.Sp = (int)sv; wk.NB = num_vblocks(n);
+  wk.W = (void *)base;        base += sv * 8;
+  wk.P = (uint32_t *)base;    base += sv * 4;
+  wk.A1 = (uint32_t *)base;   base += sv * 4;
+  wk.A2 = (uint32_t *)base;   base += sv * 4;
+  wk.ORB = keep_orbits ? (uint32_t *)base : (uint32_t *)0;
+  if (keep_orbits) base += sv * 4;
+  wk.BLK = (uint32_t *)base;
+  wk.red = red_smem;
 }
 
 // Ends of a gene given its signed position q = +-(p+1) in pi: a forward gene at position p owns
@@ -595,6 +732,37 @@ dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict
     }
     EndsFromRows ends; ends.gamma = genomes + (long long)gi * n; ends.tail = stage;
     Stats st = dist_core<NT, EPT, false>(wk, n, ends);
+    if (threadIdx.x == 0) {
+      if (stride == 1) out[p] = st.d;
+      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
+    }
+  }
+}
+
+// ends() for the large build: gamma and the signed inverse of pi both read from global memory
+struct EndsFromRowsGlobal {
+  const int32_t *gamma; const int32_t *sinv_pi;
+  __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
+    const int g = gamma[t];
+    const int s = sinv_pi[(g > 0 ? g : -g) - 1];
+    ends_from_signed_pos(g > 0 ? s : -s, L, R);
+  }
+};
+
+// Batched distance for num_genes beyond the shared-memory build: one block per pair, workspace
+// scratch + blockIdx.x * large_work_bytes(n) in global memory.
+__global__ void __launch_bounds__(1024)
+dist_pairs_large_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                        const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
+                        int stride, unsigned char *scratch) {
+  __shared__ unsigned long long red[34];
+  WorkT<uint32_t> wk;
+  large_work_carve(wk, scratch + (size_t)blockIdx.x * large_work_bytes(n, false), n, false, red);
+  for (long long p = blockIdx.x; p < npairs; p += gridDim.x) {
+    EndsFromRowsGlobal ends;
+    ends.gamma = genomes + (long long)pairs[2 * p] * n;
+    ends.sinv_pi = sinv + (long long)pairs[2 * p + 1] * n;
+    Stats st = dist_core_large<false>(wk, n, ends);
     if (threadIdx.x == 0) {
       if (stride == 1) out[p] = st.d;
       else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }

@@ -1,8 +1,9 @@
 // grsr_scenario.cuh -- device code of the sorting-by-reversals scenario search (sm_100a).
 //
 // One thread block owns one (source, destination) pair for the whole scenario and keeps the
-// current permutation, the destination's signed inverse and the breakpoint graph in shared memory;
-// blocks take pairs from a global ticket counter, so a launch sorts many pairs concurrently.
+// current permutation, the destination's signed inverse and the breakpoint graph on chip (shared
+// memory) -- or, for genomes too long for that, in an L2-resident global workspace; blocks take
+// pairs from a global ticket counter, so a launch sorts many pairs concurrently.
 // It reproduces, step for step, the reference's default -s engine:
 //
 //   print_scenario_2   G/opt_scenario.c:227-290   outer loop: rebuild G0 = graph(gamma = dest,
@@ -15,60 +16,52 @@
 //
 // "graphdist even" is evaluated in O(1): vertices x and y are an even number of edges apart
 // (walking black edge first) exactly when they lie on the same orbit of sigma(v) = grey[v ^ 1],
-// and dist_core<true> leaves every vertex's orbit label in ORB.  The candidate scan is a parallel
-// arg-min over the breakpoint list instead of the reference's O(n^2) double loop; rejected
+// and dist_core<keep orbits> leaves every vertex's orbit label in ORB.  The candidate scan is a
+// parallel arg-min over the breakpoint list instead of the reference's O(n^2) double loop; rejected
 // candidates are resumed from in key order, so the accepted reversal is the reference's.
 #pragma once
 #include "grsr_core.cuh"
 
 namespace grsr {
 
-static const unsigned kNoKey = 0xFFFFFFFFu;
-static const int kKeyShift = 14;             // key = (j - i) << 14 | i ; n <= kMaxSmemGenes < 2^14
-
-__host__ __device__ inline size_t scen_arr_bytes(int n) { return (((size_t)n + 2) * 2 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t scen_extra_bytes(int n) { return 5 * scen_arr_bytes(n); }
-
-__device__ inline unsigned blk_min_u32(unsigned v, unsigned long long *red) {
-  v = __reduce_min_sync(kFull, v);
+__device__ inline unsigned long long blk_min_u64(unsigned long long v, unsigned long long *red) {
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long x = __shfl_down_sync(kFull, v, o);
+    v = (x < v) ? x : v;
+  }
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (lane == 0) red[wid] = v;
   __syncthreads();
   if (wid == 0) {
-    v = (lane < nw) ? (unsigned)red[lane] : kNoKey;
-    v = __reduce_min_sync(kFull, v);
+    v = (lane < nw) ? red[lane] : ~0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+      unsigned long long x = __shfl_down_sync(kFull, v, o);
+      v = (x < v) ? x : v;
+    }
     if (lane == 0) red[32] = v;
   }
   __syncthreads();
-  v = (unsigned)red[32];
+  v = red[32];
   __syncthreads();
   return v;
 }
 
-// rho0(i): signed position in the destination of the gene at position i of the current genome
-struct RhoCurrent {
-  const int16_t *cur; const int16_t *sdst;
-  __device__ inline int operator()(int i) const {
-    int g = cur[i];
-    int s = sdst[(g > 0 ? g : -g) - 1];
-    return g > 0 ? s : -s;
-  }
-};
-
 // ends() of G0 = graph(gamma = destination, pi = current) (G/opt_scenario.c:229): the signed
 // position in the current genome of the destination's t-th gene is the inverse of rho0.
+template <class SV>
 struct EndsG0 {
-  const int16_t *inv0;
+  const SV *inv0;
   __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
-    ends_from_signed_pos(inv0[t], L, R);
+    ends_from_signed_pos((int)inv0[t], L, R);
   }
 };
 
 // ends() of the trial evaluation invdist_noncircular(trial, dest) (G/opt_scenario.c:980), gamma =
 // trial = current with [i..j] reversed and negated (G/scenario.c:475-486), pi = destination:
 // signed position in the destination of trial's t-th gene.
+template <class SV>
 struct EndsTrial {
-  const int16_t *rho0; int i, j;
+  const SV *rho0; int i, j;
   __device__ inline void operator()(int t, unsigned &L, unsigned &R) const {
     const int q = (t >= i && t <= j) ? -(int)rho0[i + j - t] : (int)rho0[t];
     ends_from_signed_pos(q, L, R);
@@ -79,55 +72,75 @@ struct EndsTrial {
 #define GRSR_SCEN_OVERFLOW  1   /* more steps than max_steps */
 #define GRSR_SCEN_STUCK     2   /* no candidate reduces the distance (reference: S_FAIL) */
 
+// Policy of the shared-memory build: 16-bit ids and values, register-resident jumping.
+template <int NT, int EPT>
+struct ScenSmall {
+  typedef uint16_t vid;
+  typedef int16_t sval;
+  typedef WorkT<uint16_t> work;
+  template <bool kKeep, class E>
+  static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core<NT, EPT, kKeep>(wk, n, e); }
+};
+
+// Policy of the global-memory build: 32-bit ids and values.
+struct ScenLarge {
+  typedef uint32_t vid;
+  typedef int32_t sval;
+  typedef WorkT<uint32_t> work;
+  template <bool kKeep, class E>
+  static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core_large<kKeep>(wk, n, e); }
+};
+
+// The scenario of every pair this block draws from the ticket.  CUR, SDST, INV0, RHO0: n values
+// each; BPL: n+1 ids; they and wk live wherever the policy's kernel put them.
 // steps: npairs x max_steps (start, end) pairs; nsteps/status: per pair; evals: per pair number of
 // full trial evaluations (diagnostic, may be null); ticket: zero-initialised work counter.
-template <int NT, int EPT>
-__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
-scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
-                int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
-                int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                unsigned int *ticket) {
-  GRSR_DYN_SMEM(smem_raw);
-  Work wk;
-  work_carve(wk, smem_raw, n, NT * EPT, true);
-  unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, true);
-  int16_t *CUR = (int16_t *)extra;
-  int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
-  int16_t *INV0 = (int16_t *)(extra + 2 * scen_arr_bytes(n));
-  int16_t *RHO0 = (int16_t *)(extra + 3 * scen_arr_bytes(n));
-  vid_t *BPL = (vid_t *)(extra + 4 * scen_arr_bytes(n));
-  const vid_t *ORB = wk.ORB;
-  const int tid = threadIdx.x, nt = NT;
-  __shared__ int s_pair;
+template <class Pol>
+__device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval *CUR,
+                                     typename Pol::sval *SDST, typename Pol::sval *INV0,
+                                     typename Pol::sval *RHO0, typename Pol::vid *BPL,
+                                     const int32_t *__restrict__ src, const int32_t *__restrict__ dst,
+                                     int npairs, int n, int32_t *__restrict__ steps,
+                                     int32_t *__restrict__ nsteps, int max_steps,
+                                     int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
+                                     unsigned int *ticket, int *s_pair) {
+  typedef typename Pol::sval SV;
+  typedef typename Pol::vid VT;
+  constexpr unsigned kNone = none_of<VT>();
+  const unsigned long long kNoKey = ~0ull;
+  const VT *ORB = wk.ORB;
+  const int tid = threadIdx.x, nt = blockDim.x;
 
   for (;;) {
-    if (tid == 0) s_pair = (int)atomicAdd(ticket, 1u);
+    if (tid == 0) *s_pair = (int)atomicAdd(ticket, 1u);
     __syncthreads();
-    const int p = s_pair;
+    const int p = *s_pair;
     __syncthreads();
     if (p >= npairs) break;
 
     const int32_t *ps = src + (long long)p * n, *pd = dst + (long long)p * n;
     for (int i = tid; i < n; i += nt) {
-      CUR[i] = (int16_t)ps[i];
+      CUR[i] = (SV)ps[i];
       int g = pd[i];
-      SDST[(g > 0 ? g : -g) - 1] = (int16_t)(g > 0 ? (i + 1) : -(i + 1));
+      SDST[(g > 0 ? g : -g) - 1] = (SV)(g > 0 ? (i + 1) : -(i + 1));
     }
     __syncthreads();
 
     int ns = 0, code = GRSR_SCEN_OK;
     unsigned long long nevals = 0;
-    RhoCurrent rho0; rho0.cur = CUR; rho0.sdst = SDST;
     for (;;) {
-      // rho0 and its inverse: G0 and every trial of this step are written from these two arrays
+      // rho0 (signed position in the destination of the gene at position i of the current genome)
+      // and its inverse: G0 and every trial of this step are written from these two arrays
       for (int i = tid; i < n; i += nt) {
-        int r = rho0(i);
-        RHO0[i] = (int16_t)r;
-        INV0[(r > 0 ? r : -r) - 1] = (int16_t)(r > 0 ? (i + 1) : -(i + 1));
+        int g = CUR[i];
+        int s = SDST[(g > 0 ? g : -g) - 1];
+        int r = g > 0 ? s : -s;
+        RHO0[i] = (SV)r;
+        INV0[(r > 0 ? r : -r) - 1] = (SV)(r > 0 ? (i + 1) : -(i + 1));
       }
       __syncthreads();
-      EndsG0 eg; eg.inv0 = INV0;
-      const Stats g0 = dist_core<NT, EPT, true>(wk, n, eg);   // G/opt_scenario.c:229
+      EndsG0<SV> eg; eg.inv0 = INV0;
+      const Stats g0 = Pol::template dist<true>(wk, n, eg);   // G/opt_scenario.c:229
       if (g0.d == 0) break;
       if (ns >= max_steps) { code = GRSR_SCEN_OVERFLOW; break; }
 
@@ -139,16 +152,16 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
       }, BPL, wk.red);
       const bool filter = (g0.h == 0);                        // G/opt_scenario.c:951
 
-      unsigned lastkey = kNoKey;
+      unsigned long long lastkey = kNoKey;
       int fi = -1, fj = -1;
       for (;;) {
         // smallest key (j - i, i) greater than lastkey among admissible candidates
-        unsigned best = kNoKey;
+        unsigned long long best = kNoKey;
         for (int t = tid; t < nbp; t += nt) {
-          int e1 = BPL[t];
+          int e1 = (int)BPL[t];
           int s = t + 1;
           if (lastkey != kNoKey) {
-            int g = (int)(lastkey >> kKeyShift), i0 = (int)(lastkey & ((1u << kKeyShift) - 1u));
+            int g = (int)(lastkey >> 32), i0 = (int)(lastkey & 0xFFFFFFFFull);
             int lb = e1 + 1 + g + (e1 > i0 ? 0 : 1);          // smallest admissible right edge
             int lo = t + 1, hi = nbp;
             while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)BPL[mid] < lb) lo = mid + 1; else hi = mid; }
@@ -159,16 +172,17 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
             while (s < nbp && ORB[2 * (int)BPL[s]] != want) s++;
           }
           if (s < nbp) {
-            int e2 = BPL[s];
-            best = min(best, ((unsigned)(e2 - e1 - 1) << kKeyShift) | (unsigned)e1);
+            int e2 = (int)BPL[s];
+            unsigned long long key = ((unsigned long long)(unsigned)(e2 - e1 - 1) << 32) | (unsigned)e1;
+            best = (key < best) ? key : best;
           }
         }
-        best = blk_min_u32(best, wk.red);
+        best = blk_min_u64(best, wk.red);
         if (best == kNoKey) break;
-        const int i = (int)(best & ((1u << kKeyShift) - 1u));
-        const int j = i + (int)(best >> kKeyShift);
-        EndsTrial et; et.rho0 = RHO0; et.i = i; et.j = j;
-        const Stats t1 = dist_core<NT, EPT, false>(wk, n, et);  // G/opt_scenario.c:974-986
+        const int i = (int)(best & 0xFFFFFFFFull);
+        const int j = i + (int)(best >> 32);
+        EndsTrial<SV> et; et.rho0 = RHO0; et.i = i; et.j = j;
+        const Stats t1 = Pol::template dist<false>(wk, n, et);  // G/opt_scenario.c:974-986
         nevals++;
         if (t1.d == g0.d - 1) { fi = i; fj = j; break; }
         lastkey = best;
@@ -178,8 +192,8 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
       // current <- trial (G/opt_scenario.c:283-285)
       for (int k = tid; 2 * k <= fj - fi; k += nt) {
         int a = fi + k, b = fj - k;
-        int16_t x = CUR[a], y = CUR[b];
-        CUR[a] = (int16_t)(-y); CUR[b] = (int16_t)(-x);
+        SV x = CUR[a], y = CUR[b];
+        CUR[a] = (SV)(-y); CUR[b] = (SV)(-x);
       }
       if (tid == 0) {
         int32_t *o = steps + 2 * ((long long)p * max_steps + ns);
@@ -194,6 +208,55 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
     }
     __syncthreads();
   }
+}
+
+__host__ __device__ inline size_t scen_arr_bytes(int n) { return (((size_t)n + 2) * 2 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t scen_extra_bytes(int n) { return 5 * scen_arr_bytes(n); }
+
+template <int NT, int EPT>
+__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
+scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
+                int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
+                int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
+                unsigned int *ticket) {
+  GRSR_DYN_SMEM(smem_raw);
+  Work wk;
+  work_carve(wk, smem_raw, n, NT * EPT, true);
+  unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, true);
+  int16_t *CUR = (int16_t *)extra;
+  int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
+  int16_t *INV0 = (int16_t *)(extra + 2 * scen_arr_bytes(n));
+  int16_t *RHO0 = (int16_t *)(extra + 3 * scen_arr_bytes(n));
+  uint16_t *BPL = (uint16_t *)(extra + 4 * scen_arr_bytes(n));
+  __shared__ int s_pair;
+  scenario_body<ScenSmall<NT, EPT> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
+                                     max_steps, status, evals, ticket, &s_pair);
+}
+
+__host__ __device__ inline size_t scen_large_arr_bytes(int n) { return (((size_t)n + 2) * 4 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t scen_large_bytes(int n) {
+  return ((large_work_bytes(n, true) + 5 * scen_large_arr_bytes(n)) + 255) & ~(size_t)255;
+}
+
+// global-memory build: scratch + blockIdx.x * scen_large_bytes(n) is this block's workspace
+__global__ void __launch_bounds__(1024)
+scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
+                      int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
+                      int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
+                      unsigned int *ticket, unsigned char *scratch) {
+  __shared__ unsigned long long red[34];
+  __shared__ int s_pair;
+  unsigned char *base = scratch + (size_t)blockIdx.x * scen_large_bytes(n);
+  WorkT<uint32_t> wk;
+  large_work_carve(wk, base, n, true, red);
+  unsigned char *extra = base + large_work_bytes(n, true);
+  int32_t *CUR = (int32_t *)extra;
+  int32_t *SDST = (int32_t *)(extra + scen_large_arr_bytes(n));
+  int32_t *INV0 = (int32_t *)(extra + 2 * scen_large_arr_bytes(n));
+  int32_t *RHO0 = (int32_t *)(extra + 3 * scen_large_arr_bytes(n));
+  uint32_t *BPL = (uint32_t *)(extra + 4 * scen_large_arr_bytes(n));
+  scenario_body<ScenLarge>(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
+                           max_steps, status, evals, ticket, &s_pair);
 }
 
 } // namespace grsr

@@ -30,7 +30,7 @@ extern "C" {
 #define GRSR_ERR_INVALID   (-1)  /* bad argument, or a genome that is not a signed permutation */
 #define GRSR_ERR_CUDA      (-2)  /* CUDA runtime error */
 #define GRSR_ERR_NODEVICE  (-3)  /* no CUDA device / requested device missing */
-#define GRSR_ERR_TOOLARGE  (-4)  /* num_genes beyond what this build's kernels hold on chip */
+#define GRSR_ERR_TOOLARGE  (-4)  /* num_genes beyond grsr_max_genes() */
 #define GRSR_ERR_NOMEM     (-5)
 #define GRSR_ERR_SEARCH    (-6)  /* scenario search found no distance-reducing reversal
                                     (reference prints "ERROR: reversals ended prematurely",
@@ -56,8 +56,9 @@ typedef struct {
 int grsr_abi_version(void);
 const char *grsr_last_error(void);
 int grsr_device_count(void);           /* number of CUDA devices, 0 if none, never fails */
-int grsr_max_genes(void);              /* largest num_genes the scenario kernels of this build accept
-                                          (distances alone accept up to 14000) */
+int grsr_max_genes(void);              /* largest num_genes accepted (global-memory build) */
+int grsr_max_genes_on_chip(int scenario); /* largest num_genes served by the shared-memory build
+                                          (scenario != 0: by the scenario kernels) */
 void grsr_release(void);               /* frees the device buffers the host-buffer entry points keep
                                           between calls */
 

@@ -34,3 +34,30 @@ extern "C" int emu_scenario(const int32_t *src, const int32_t *dst, int npairs, 
   }));
   return 0;
 }
+
+// the global-memory ("large") build, run at small n to check its logic
+extern "C" int emu_dist_pairs_large(const int32_t *genomes, int G, int n, const int32_t *pairs,
+                                    long long npairs, int32_t *out, int stride, int threads, int grid) {
+  std::vector<int32_t> sinv((size_t)G * n);
+  long long total = (long long)G * n;
+  int32_t *sp = sinv.data();
+  emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
+  std::vector<unsigned char> scratch(grsr::large_work_bytes(n, false) * (size_t)grid + 64);
+  unsigned char *sc = scratch.data();
+  emu::launch((unsigned)grid, (unsigned)threads, 0, [&] {
+    grsr::dist_pairs_large_kernel(genomes, sp, n, pairs, npairs, out, stride, sc);
+  });
+  return 0;
+}
+
+extern "C" int emu_scenario_large(const int32_t *src, const int32_t *dst, int npairs, int n, int32_t *steps,
+                                  int32_t *nsteps, int max_steps, int32_t *status,
+                                  unsigned long long *evals, int threads, int grid) {
+  unsigned int ticket = 0;
+  std::vector<unsigned char> scratch(grsr::scen_large_bytes(n) * (size_t)grid + 64);
+  unsigned char *sc = scratch.data();
+  emu::launch((unsigned)grid, (unsigned)threads, 0, [&] {
+    grsr::scenario_large_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, sc);
+  });
+  return 0;
+}
