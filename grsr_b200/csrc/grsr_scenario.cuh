@@ -154,8 +154,13 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
 
       unsigned long long lastkey = kNoKey;
       int fi = -1, fj = -1;
+      // smallest reversal length found so far in the current search, shared by the block: a lane
+      // whose orbit partner is far away stops scanning as soon as somebody has a shorter candidate
+      volatile unsigned *bound = (volatile unsigned *)&wk.red[33];
       for (;;) {
         // smallest key (j - i, i) greater than lastkey among admissible candidates
+        if (tid == 0) *bound = 0xFFFFFFFFu;
+        __syncthreads();
         unsigned long long best = kNoKey;
         for (int t = tid; t < nbp; t += nt) {
           int e1 = (int)BPL[t];
@@ -167,14 +172,22 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
             while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)BPL[mid] < lb) lo = mid + 1; else hi = mid; }
             s = lo;
           }
+          int e2 = -1;
           if (filter) {
-            unsigned want = ORB[2 * e1 + 1];
-            while (s < nbp && ORB[2 * (int)BPL[s]] != want) s++;
+            const unsigned want = ORB[2 * e1 + 1];
+            for (; s < nbp; s++) {
+              const int c = (int)BPL[s];
+              if ((unsigned)(c - e1 - 1) > *bound) break;     // cannot beat a candidate already found
+              if (ORB[2 * c] == want) { e2 = c; break; }
+            }
+          } else if (s < nbp) {
+            e2 = (int)BPL[s];
           }
-          if (s < nbp) {
-            int e2 = (int)BPL[s];
-            unsigned long long key = ((unsigned long long)(unsigned)(e2 - e1 - 1) << 32) | (unsigned)e1;
+          if (e2 >= 0) {
+            const unsigned len0 = (unsigned)(e2 - e1 - 1);
+            unsigned long long key = ((unsigned long long)len0 << 32) | (unsigned)e1;
             best = (key < best) ? key : best;
+            atomicMin((unsigned *)&wk.red[33], len0);
           }
         }
         best = blk_min_u64(best, wk.red);
