@@ -26,8 +26,14 @@
 
 #ifdef GRSR_EMU
 #define GRSR_DYN_SMEM(name) unsigned char *name = emu::dyn_smem()
+// The emulator runs one thread at a time, which would let late threads of a jumping round see
+// words already updated in that round (the most favourable schedule).  This extra barrier between
+// the gathers and the stores forces the least favourable one -- everybody reads before anybody
+// writes -- so that the round count is tested against the guaranteed doubling only.
+#define GRSR_EMU_READ_BEFORE_WRITE() __syncthreads()
 #else
 #define GRSR_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define GRSR_EMU_READ_BEFORE_WRITE() ((void)0)
 #endif
 
 namespace grsr {
@@ -492,6 +498,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
         uint32_t U[UB];
 #pragma unroll
         for (int j = 0; j < UB; j++) U[j] = *(const uint32_t *)(Wb + (R[j0 + j] & 0x1FFFCu));
+        GRSR_EMU_READ_BEFORE_WRITE();
 #pragma unroll
         for (int j = 0; j < UB; j++) {
           const uint32_t w = R[j0 + j], wu = U[j];
@@ -598,12 +605,14 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
     const int rounds = ceil_log2(n + 1);
     for (int r = 0; r < rounds; r++) {
       unsigned long long chg = 0;
-      for (int v0 = tid; v0 < S; v0 += 4 * nt) {
+      for (int vb = 0; vb < S; vb += 4 * nt) {
+        const int v0 = vb + tid;
         unsigned long long w[4], u[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { int v = v0 + j * nt; w[j] = (v < S) ? W[v] : 0ull; }
 #pragma unroll
         for (int j = 0; j < 4; j++) { int v = v0 + j * nt; u[j] = (v < S) ? W[GRSR_L_NEXT(w[j])] : 0ull; }
+        GRSR_EMU_READ_BEFORE_WRITE();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int v = v0 + j * nt;
