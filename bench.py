@@ -332,6 +332,7 @@ def run_gpu_arm(args):
             if not np.array_equal(d_cpu, o_np[:len(sample)]):
                 raise SystemExit("GPU distances differ from the CPU reference on the baseline sample")
             cpu["checked"] = "GPU distances equal the CPU reference on all %d sample pairs" % len(sample)
+        scen = scenario_leg(capi) if (world == 1 and not args.no_cpu and not args.no_scenario) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -342,11 +343,66 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(genomes.nbytes) * world,
                     "d2h_bytes_per_step": int(P * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "grsr_dist_matrix_shard (host buffers, pinned)"},
-            "gpu_launches": args.steps * world, "clocks": clocks,
+            "gpu_launches": args.steps * world, "clocks": clocks, "scenario": scen,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---- scenario leg (secondary metric of BASELINE.json: scenario reversals/s) ---------------------------
+
+def _ref_scenario_worker(args):
+    """One reference scenario in a worker process (the reference prints through a global FILE*)."""
+    src, dst = args
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so"))
+    n = len(src)
+    steps = np.zeros(2 * (n + 2), dtype=np.int32)
+    k = lib.ref_scenario(src.ctypes.data_as(I32P), dst.ctypes.data_as(I32P), n, steps.ctypes.data_as(I32P), n + 2)
+    return steps[:2 * max(k, 0)].reshape(-1, 2)
+
+
+def scenario_leg(capi):
+    """Reversals/s of grsr_scenario_batch (host buffers in, step lists out) on two bounded samples:
+    config-4-sized random pairs, and hurdle/fortress-rich pairs (where the reference brute-forces
+    every breakpoint pair); the latter is also timed on the reference CPU and compared step by step."""
+    import random
+    from concurrent.futures import ProcessPoolExecutor
+    out = {}
+    rng = random.Random(4)
+    n, k = 5000, 148
+    src = np.array([gen.random_signed_perm(n, rng) for _ in range(k)], dtype=np.int32)
+    dst = np.tile(np.arange(1, n + 1, dtype=np.int32), (k, 1))
+    capi.scenario_batch(src[:2], dst[:2])
+    t0 = time.perf_counter()
+    steps = capi.scenario_batch(src, dst)
+    dt = time.perf_counter() - t0
+    tot = sum(len(x) for x in steps)
+    out["random_n5000"] = {"pairs": k, "genes": n, "reversals": tot, "seconds": dt, "value": tot / dt,
+                           "unit": "reversals/s", "roofline_frac_hbm": tot / dt * (12 * n + 16) / 6554.6e9}
+    n, k = 300, 2368
+    src = np.array([gen.hurdle_rich_perm(n, 9000 + s) for s in range(k)], dtype=np.int32)
+    dst = np.tile(np.arange(1, n + 1, dtype=np.int32), (k, 1))
+    t0 = time.perf_counter()
+    steps = capi.scenario_batch(src, dst)
+    dt = time.perf_counter() - t0
+    tot = sum(len(x) for x in steps)
+    leg = {"pairs": k, "genes": n, "reversals": tot, "seconds": dt, "value": tot / dt, "unit": "reversals/s"}
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")):
+        cores = os.cpu_count() or 1
+        m = min(k, 2 * cores)
+        t0 = time.perf_counter()
+        with ProcessPoolExecutor(max_workers=cores) as ex:
+            ref = list(ex.map(_ref_scenario_worker, [(src[q], dst[q]) for q in range(m)]))
+        rdt = time.perf_counter() - t0
+        if not all(np.array_equal(a, b) for a, b in zip(ref, steps[:m])):
+            raise SystemExit("GPU scenarios differ from the CPU reference on the scenario sample")
+        rtot = sum(len(x) for x in ref)
+        leg["cpu_baseline"] = {"value": rtot / rdt, "unit": "reversals/s", "cores": cores, "kind": "reference",
+                               "sample": "first %d pairs, one process per pair on %d cores, %.1f s; step lists equal"
+                                         % (m, cores, rdt)}
+    out["hurdle_rich_n300"] = leg
+    return out
 
 
 def main():
@@ -355,7 +411,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="grsr", choices=["grsr", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and scenario legs")
+    ap.add_argument("--no-scenario", action="store_true", help="skip the scenario leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -225,11 +225,26 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   //     (a cycle that starts left of P and reaches into it) and the largest reach (a cycle that
   //     reaches into P and ends right of it).  Those two neighbours are enough to recover the
   //     components of the reference's stack sweep (G/graph_components.c:101-138).
+  //     A short extent is scanned by the cycle's own lane; long ones are handed to the whole warp.
   for (int base = tid & ~31; base <= n; base += nt) {
     int k = base + lane;
-    unsigned r0 = 0, R0 = 0; bool isroot = false;
+    unsigned r0 = 0, R0 = 0; bool isroot = false, big = false;
     if (k <= n) { r0 = 2u * k; isroot = (A2[r0] == r0); if (isroot) R0 = W[r0 + 1]; }
-    unsigned todo = __ballot_sync(kFull, isroot);
+    if (isroot) {
+      big = (R0 - r0) > 48u;
+      if (!big) {
+        unsigned mn = kNone, mx = 0;
+        for (unsigned v = r0 + 1; v < R0; v++) {
+          unsigned c = A2[v];
+          if (c != kNone) { mn = min(mn, c); mx = max(mx, W[c + 1]); }
+        }
+        unsigned lk1 = (mn < r0) ? mn : kNoLink;
+        unsigned lk2 = (mx > R0) ? (unsigned)A2[mx] : kNone;
+        A1[r0] = (VT)((A1[r0] & 1u) | lk1);
+        A1[r0 + 1] = (VT)lk2;
+      }
+    }
+    unsigned todo = __ballot_sync(kFull, isroot && big);
     while (todo) {
       int src = __ffs((int)todo) - 1; todo &= todo - 1;
       unsigned rr = __shfl_sync(kFull, r0, src), RR = __shfl_sync(kFull, R0, src);
@@ -389,7 +404,7 @@ template <class WordFn>
 __device__ inline bool unoriented_cycles_all_covered(int n, int S, WordFn word) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   int unresolved = 0;
-  for (int base = tid & ~31; base <= n; base += nt) {
+  for (int base = tid & ~31; base <= n && !unresolved; base += nt) {
     const int k = base + lane;
     const unsigned q = 2u * k;
     bool isq = false;
@@ -417,7 +432,7 @@ __device__ inline bool unoriented_cycles_all_covered(int n, int S, WordFn word) 
         const unsigned mh = __ballot_sync(kFull, st == 1), ms = __ballot_sync(kFull, st == 2);
         if (mh | ms) { hit = mh && (!ms || __ffs((int)mh) < __ffs((int)ms)); break; }
       }
-      if (!hit) unresolved = 1;
+      if (!hit) { unresolved = 1; break; }            // one unsettled cycle decides: stop probing
     }
   }
   return !__syncthreads_or(unresolved);
