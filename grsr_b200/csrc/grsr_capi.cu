@@ -149,23 +149,64 @@ int check_genes_fit(int n) {
   return GRSR_OK;
 }
 
-// grid and per-block scratch of the large build: one 1024-thread block per resident slot
-template <class K>
-int plan_large(K kernel, long long units, size_t bytes_per_block, int dev, int *grid, void **scratch) {
+// Plan of the global-memory build.  With many pairs every pair gets one 1024-thread block; with few
+// pairs (fewer than SMs) each pair gets a thread-block cluster of cs = 2..16 blocks (SMs) instead, so
+// that a single long scenario still uses a good part of the chip.  scratch / xch come from the
+// device's buffer cache (slots 4 and 5).
+struct LargePlan { int cs; int teams; int grid; void *scratch; void *xch; };
+
+template <class KB, class KC>
+int plan_large(KB block_kernel, KC cluster_kernel, long long units, size_t bytes_per_team, int dev,
+               LargePlan &P) {
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 1024, 0));
-  if (occ < 1) return fail(GRSR_ERR_CUDA, "large kernel does not fit on an SM");
-  long long g = (long long)di.sms * occ;
-  if (g > units) g = units;
-  if (g < 1) g = 1;
-  *grid = (int)g;
   if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
+  int cs = 1;
+  while (cs < 16 && (long long)cs * 2 * units <= di.sms) cs *= 2;
+  int forced = env_int("GRSR_CLUSTER", 0);
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8 || forced == 16) cs = forced;
+  P.cs = cs;
+  if (cs == 1) {
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, block_kernel, 1024, 0));
+    if (occ < 1) return fail(GRSR_ERR_CUDA, "large kernel does not fit on an SM");
+    long long g = (long long)di.sms * occ;
+    if (g > units) g = units;
+    if (g < 1) g = 1;
+    P.teams = (int)g; P.grid = (int)g;
+  } else {
+    if (cs > 8) CK(cudaFuncSetAttribute(cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(cs); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 34 * 8;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int maxc = 0;
+    CK(cudaOccupancyMaxActiveClusters(&maxc, cluster_kernel, &cfg));
+    if (maxc < 1) return fail(GRSR_ERR_CUDA, "a cluster of %d blocks does not fit on this device", cs);
+    long long t = maxc;
+    if (t > units) t = units;
+    if (t < 1) t = 1;
+    P.teams = (int)t; P.grid = (int)t * cs;
+  }
   DevCache &c = g_cache[dev];
   std::lock_guard<std::recursive_mutex> lk(c.mu);
-  return cache_reserve(c, 4, bytes_per_block * (size_t)g, scratch);
+  if ((rc = cache_reserve(c, 4, bytes_per_team * (size_t)P.teams, &P.scratch))) return rc;
+  return cache_reserve(c, 5, sizeof(unsigned long long) * grsr::kXchWords * (size_t)P.teams, &P.xch);
+}
+
+template <class K, class... Args>
+int launch_cluster(K kernel, const LargePlan &P, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = P.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.gridDim = dim3(P.grid); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 34 * 8;
+  cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kernel, args...));
+  return GRSR_OK;
 }
 
 // Upper triangle enumerated column by column -- (0,1), (0,2), (1,2), (0,3), ... -- so that
@@ -300,13 +341,14 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
   const bool small = small_fits(n, true);
   Launch L;
   L.threads = 1024; L.ept = 0; L.smem = 0; L.grid = 1;
-  void *scratch = nullptr;
+  LargePlan LP = {1, 1, 1, nullptr, nullptr};
   if (small) {
     grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
     L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
   } else {
-    rc = plan_large(grsr::scenario_large_kernel, npairs, grsr::scen_large_bytes(n), dev, &L.grid, &scratch);
+    rc = plan_large(grsr::scenario_large_kernel, grsr::scenario_cluster_kernel, npairs,
+                    grsr::scen_large_bytes(n), dev, LP);
   }
   if (rc) return rc;
   cudaStream_t st;
@@ -329,11 +371,18 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
       GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
           (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
           (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
-    } else {
-      grsr::scenario_large_kernel<<<L.grid, 1024, 0, st>>>(
+    } else if (LP.cs == 1) {
+      grsr::scenario_large_kernel<<<LP.grid, 1024, 0, st>>>(
           (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
           (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p,
-          (unsigned char *)scratch);
+          (unsigned char *)LP.scratch);
+    } else {
+      int r = launch_cluster(grsr::scenario_cluster_kernel, LP, st,
+                             (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n,
+                             (int32_t *)dsteps.p, (int32_t *)dns.p, max_steps, (int32_t *)dstat.p,
+                             (unsigned long long *)nullptr, (unsigned int *)dtick.p,
+                             (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
+      if (r) return r;
     }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(steps, dsteps.p, sbytes, cudaMemcpyDeviceToHost, st));
@@ -428,14 +477,21 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
         d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
   } else {
-    int dev, grid;
-    void *scratch = nullptr;
+    int dev;
     CK(cudaGetDevice(&dev));
-    rc = plan_large(grsr::dist_pairs_large_kernel, npairs, grsr::large_work_bytes(num_genes, false), dev,
-                    &grid, &scratch);
+    LargePlan LP;
+    rc = plan_large(grsr::dist_pairs_large_kernel, grsr::dist_pairs_cluster_kernel, npairs,
+                    grsr::large_work_bytes(num_genes, false), dev, LP);
     if (rc) return rc;
-    grsr::dist_pairs_large_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(
-        d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride, (unsigned char *)scratch);
+    if (LP.cs == 1) {
+      grsr::dist_pairs_large_kernel<<<LP.grid, 1024, 0, (cudaStream_t)stream>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride, (unsigned char *)LP.scratch);
+    } else {
+      rc = launch_cluster(grsr::dist_pairs_cluster_kernel, LP, (cudaStream_t)stream, d_genomes, d_sinv,
+                          num_genes, d_pairs, (long long)npairs, d_out, stride,
+                          (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
+      if (rc) return rc;
+    }
   }
   CK(cudaGetLastError());
   return GRSR_OK;

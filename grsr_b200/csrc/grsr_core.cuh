@@ -23,6 +23,9 @@
 // the CPU test-suite to debug kernel logic); nothing in the product selects that build.
 #pragma once
 #include <stdint.h>
+#ifndef GRSR_EMU
+#include <cooperative_groups.h>
+#endif
 
 #ifdef GRSR_EMU
 #define GRSR_DYN_SMEM(name) unsigned char *name = emu::dyn_smem()
@@ -31,12 +34,24 @@
 // the gathers and the stores forces the least favourable one -- everybody reads before anybody
 // writes -- so that the round count is tested against the guaranteed doubling only.
 #define GRSR_EMU_READ_BEFORE_WRITE() __syncthreads()
+#define GRSR_EMU_READ_BEFORE_WRITE_TM() TM::sync()
 #else
 #define GRSR_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define GRSR_EMU_READ_BEFORE_WRITE() ((void)0)
+#define GRSR_EMU_READ_BEFORE_WRITE_TM() ((void)0)
 #endif
 
 namespace grsr {
+
+#ifdef GRSR_EMU
+__device__ inline unsigned cluster_rank() { return emu::cluster_rank(); }
+__device__ inline unsigned cluster_size() { return emu::cluster_size(); }
+__device__ inline void cluster_sync() { emu::cluster_barrier(); }
+#else
+__device__ inline unsigned cluster_rank() { return cooperative_groups::this_cluster().block_rank(); }
+__device__ inline unsigned cluster_size() { return cooperative_groups::this_cluster().num_blocks(); }
+__device__ inline void cluster_sync() { cooperative_groups::this_cluster().sync(); }
+#endif
 
 typedef uint16_t vid_t;
 static const unsigned kFull = 0xFFFFFFFFu;
@@ -70,6 +85,8 @@ struct WorkT {
   VT *ORB;                  // [S]  sigma-orbit label per vertex (scenario kernels only)
   VT *BLK;                  // [2*NB] per-32-vertex block: min cycle id, max cycle reach
   unsigned long long *red;  // [34] reduction scratch (always shared memory)
+  unsigned long long *xch;  // cluster build: global exchange area of the cluster (kXchWords), else null
+  unsigned epoch;           // cluster build: number of team collectives issued so far (buffer parity)
   int S, Sp, NB;
 };
 typedef WorkT<uint16_t> Work;
@@ -99,6 +116,7 @@ __device__ inline void work_carve(Work &wk, unsigned char *base, int n, int slot
   if (keep_orbits) base += (size_t)sv * 2;
   wk.BLK = (vid_t *)base;   base += (((size_t)wk.NB * 2 * sizeof(vid_t)) + 15) & ~(size_t)15;
   wk.red = (unsigned long long *)base;
+  wk.xch = (unsigned long long *)0; wk.epoch = 0;
 }
 
 // ---- block-wide reductions (every thread of the block must call; result returned to all) ----------
@@ -164,6 +182,106 @@ __device__ inline int blk_compact(int N, F f, VT *out, unsigned long long *red) 
   return total;
 }
 
+// --------------------------------------------------------------------------------------------------
+// Teams: the set of threads that works on one pair.  TeamBlock = one thread block (every kernel of
+// the shared-memory build and the plain global-memory build).  TeamCluster = a thread-block cluster
+// (up to 16 SMs) working on one pair of the global-memory build: same code, team-wide thread ids,
+// cluster barriers, and collectives that combine per-block partial results through a small global
+// exchange area (double-buffered by the collective count, so one cluster barrier per collective).
+// --------------------------------------------------------------------------------------------------
+struct TeamBlock {
+  static __device__ inline int tid() { return threadIdx.x; }
+  static __device__ inline int size() { return blockDim.x; }
+  static __device__ inline void sync() { __syncthreads(); }
+  template <class WK> static __device__ inline int any(int pred, WK &) { return __syncthreads_or(pred); }
+  template <class WK> static __device__ inline unsigned long long sum(unsigned long long v, WK &wk) {
+    return blk_sum_u64(v, wk.red);
+  }
+  template <class WK> static __device__ inline unsigned max32(unsigned v, WK &wk) { return blk_max_u32(v, wk.red); }
+  template <class VT, class F, class WK>
+  static __device__ inline int compact(int N, F f, VT *out, WK &wk) { return blk_compact(N, f, out, wk.red); }
+};
+
+static const int kMaxClusterBlocks = 16;
+static const int kXchWords = 2 * kMaxClusterBlocks + 2 * kMaxClusterBlocks * 32 + 8;  // u64 words
+
+struct TeamCluster {
+  static __device__ inline int tid() { return (int)(cluster_rank() * blockDim.x + threadIdx.x); }
+  static __device__ inline int size() { return (int)(cluster_size() * blockDim.x); }
+  // barrier.cluster arrive.release / wait.acquire: orders the global-memory accesses of the cluster
+  static __device__ inline void sync() { cluster_sync(); }
+  // slot of this collective in the exchange area (two alternating buffers of kMaxClusterBlocks)
+  template <class WK> static __device__ inline volatile unsigned long long *slot(WK &wk) {
+    volatile unsigned long long *p = wk.xch + (wk.epoch & 1u) * kMaxClusterBlocks;
+    wk.epoch++;
+    return p;
+  }
+  // every lane fetches one block's partial (one L2 round trip), the warp combines them
+  static __device__ inline unsigned long long part(volatile unsigned long long *x, unsigned long long dflt) {
+    const unsigned lane = threadIdx.x & 31;
+    return (lane < cluster_size()) ? x[lane] : dflt;
+  }
+  template <class WK> static __device__ inline int any(int pred, WK &wk) {
+    volatile unsigned long long *x = slot(wk);
+    int b = __syncthreads_or(pred);
+    if (threadIdx.x == 0) x[cluster_rank()] = (unsigned long long)b;
+    sync();
+    return __any_sync(kFull, part(x, 0ull) != 0ull);
+  }
+  template <class WK> static __device__ inline unsigned long long sum(unsigned long long v, WK &wk) {
+    volatile unsigned long long *x = slot(wk);
+    v = blk_sum_u64(v, wk.red);
+    if (threadIdx.x == 0) x[cluster_rank()] = v;
+    sync();
+    unsigned long long r = part(x, 0ull);
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(kFull, r, o);
+    return r;
+  }
+  template <class WK> static __device__ inline unsigned max32(unsigned v, WK &wk) {
+    volatile unsigned long long *x = slot(wk);
+    v = blk_max_u32(v, wk.red);
+    if (threadIdx.x == 0) x[cluster_rank()] = v;
+    sync();
+    return __reduce_max_sync(kFull, (unsigned)part(x, 0ull));
+  }
+  // ordered compaction over the whole team: every warp of the cluster owns a contiguous chunk
+  template <class VT, class F, class WK>
+  static __device__ inline int compact(int N, F f, VT *out, WK &wk) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int wid = (int)cluster_rank() * wpb + (threadIdx.x >> 5), nw = (int)cluster_size() * wpb;
+    volatile unsigned *cnts = (volatile unsigned *)(wk.xch + 2 * kMaxClusterBlocks) +
+                              (wk.epoch & 1u) * (kMaxClusterBlocks * 32);
+    wk.epoch++;
+    int chunk = (((N + nw - 1) / nw) + 31) & ~31;
+    int lo = wid * chunk, hi = min(N, lo + chunk);
+    int cnt = 0;
+    for (int base = lo; base < hi; base += 32) {
+      int i = base + lane; unsigned val = 0;
+      bool ok = (i < hi) && f(i, val);
+      cnt += __popc(__ballot_sync(kFull, ok));
+    }
+    if (lane == 0) cnts[wid] = (unsigned)cnt;
+    sync();
+    // counts of the warps before mine and of all warps: lanes fetch strided, the warp adds up
+    unsigned before = 0, all = 0;
+    for (int w = lane; w < nw; w += 32) { unsigned cw = cnts[w]; all += cw; if (w < wid) before += cw; }
+    unsigned long long both = ((unsigned long long)before << 32) | all;
+    for (int o = 16; o > 0; o >>= 1) both += __shfl_xor_sync(kFull, both, o);
+    int pos = (int)(both >> 32);
+    const int total = (int)(both & 0xFFFFFFFFull);
+    for (int base = lo; base < hi; base += 32) {
+      int i = base + lane; unsigned val = 0;
+      bool ok = (i < hi) && f(i, val);
+      unsigned m = __ballot_sync(kFull, ok);
+      if (ok) out[pos + __popc(m & ((1u << lane) - 1u))] = (VT)val;
+      pos += __popc(m);
+    }
+    sync();
+    return total;
+  }
+};
+
 __device__ inline int ceil_log2(int x) { int r = 0; while ((1 << r) < x) r++; return r; }
 
 // Follow parent words up to the representative (union-find forest kept in W[root]).
@@ -180,9 +298,9 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
 //              edge, else 0.  P is free (it may alias the jumping words, which are dead by now).
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
-template <class VT>
+template <class TM, class VT>
 __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int tid = TM::tid(), nt = TM::size(), lane = tid & 31;
   const int S = wk.S;
   constexpr unsigned kNone = none_of<VT>();
   constexpr unsigned kNoLink = kNone & ~1u;
@@ -195,7 +313,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     unsigned a = 2u * k;
     if (A2[a] == a) { W[a] = a; W[a + 1] = 0; }
   }
-  __syncthreads();
+  TM::sync();
 
   // S2: reach of every cycle = max vertex carrying its id (reference: right[], G/graph_edit.c:392).
   //     Lanes hold consecutive vertices, so the highest lane of each equal-id group carries the max.
@@ -205,7 +323,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     unsigned grp = __match_any_sync(kFull, c);
     if (c != kNone && lane == 31 - __clz((int)grp)) atomicMax(&W[c + 1], (uint32_t)v);
   }
-  __syncthreads();
+  TM::sync();
 
   // S3: per block of 32 vertices: smallest cycle id and largest reach seen in it.
   for (int B = tid; B < wk.NB; B += nt) {
@@ -219,7 +337,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     }
     bmin[B] = (VT)mn; bmax[B] = (VT)mx;
   }
-  __syncthreads();
+  TM::sync();
 
   // S4: for every cycle P = (l, r): among the vertices strictly inside (l, r), the smallest cycle id
   //     (a cycle that starts left of P and reaches into it) and the largest reach (a cycle that
@@ -278,7 +396,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
       }
     }
   }
-  __syncthreads();
+  TM::sync();
 
   // S5: connected components of the cycles under those links: hook larger root under smaller,
   //     compress, repeat until no link joins two trees.
@@ -299,12 +417,12 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
         if (o != me) { atomicMin(&W[max(o, me)], min(o, me)); changed = 1; }
       }
     }
-    if (!__syncthreads_or(changed)) break;
+    if (!TM::any(changed, wk)) break;
     for (int k = tid; k <= n; k += nt) {
       unsigned r = 2u * k;
       if (A2[r] == r) W[r] = uf_find(W, r);
     }
-    __syncthreads();
+    TM::sync();
   }
 
   // S6: a component is oriented iff one of its cycles is (G/graph_components.c:309-336).
@@ -313,46 +431,46 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     unsigned r = 2u * k;
     if (A2[r] == r) W[r + 1] = 0;
   }
-  __syncthreads();
+  TM::sync();
   for (int k = tid; k <= n; k += nt) {
     unsigned r = 2u * k;
     if (A2[r] == r && (A1[r] & 1u)) W[W[r] + 1] = 1;
   }
-  __syncthreads();
+  TM::sync();
 
   // S7: the vertices of unoriented components, in vertex order, as a list of component ids
   //     (the filtered scan of G/graph_components.c:566-585).
-  int m = blk_compact(S, [&](int v, unsigned &val) -> bool {
+  int m = TM::compact(S, [&](int v, unsigned &val) -> bool {
     unsigned c = A2[v];
     if (c == kNone) return false;
     unsigned comp = W[c];
     if (W[comp + 1]) return false;
     val = comp; return true;
-  }, A1, wk.red);
+  }, A1, wk);
   if (m == 0) return 0;
 
   // S8: runs of equal ids = the reference's "blocks"; keep one entry per run.
-  int nb = blk_compact(m, [&](int t, unsigned &val) -> bool {
+  int nb = TM::compact(m, [&](int t, unsigned &val) -> bool {
     unsigned c = A1[t];
     if (t > 0 && A1[t - 1] == c) return false;
     val = c; return true;
-  }, A2, wk.red);
+  }, A2, wk);
   const VT *run = A2;
 
   // S9: per component: number of runs (W[c]) and 1 + index of its last run (W[c+1]).
   for (int t = tid; t < nb; t += nt) { unsigned c = run[t]; W[c] = 0; W[c + 1] = 0; }
-  __syncthreads();
+  TM::sync();
   for (int t = tid; t < nb; t += nt) {
     unsigned c = run[t];
     atomicAdd(&W[c], 1u);
     atomicMax(&W[c + 1], (uint32_t)(t + 1));
   }
-  __syncthreads();
+  TM::sync();
   const unsigned first = run[0], last = run[nb - 1];
   // 1 + index of the last-but-one run of the final component (needed for its "right" neighbour)
   unsigned pl = 0;
   for (int t = tid; t < nb - 1; t += nt) if (run[t] == last) pl = max(pl, (unsigned)(t + 1));
-  const unsigned prevlast = blk_max_u32(pl, wk.red);
+  const unsigned prevlast = TM::max32(pl, wk);
 
   // Hurdles (one run), greatest hurdle (first == last with two runs), super-hurdles
   // (G/graph_components.c:603-624, 640-656, 674-694).  left/right are the reference's
@@ -383,7 +501,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     if (right_first == last && hf && !hl) scount++;
     else if (left_last == first && hl && !hf) scount++;
   }
-  unsigned long long tot = blk_sum_u64(((unsigned long long)hcount << 32) | scount, wk.red);
+  unsigned long long tot = TM::sum(((unsigned long long)hcount << 32) | scount, wk);
   unsigned h = (unsigned)(tot >> 32), s = (unsigned)(tot & 0xFFFFFFFFu);
   unsigned f = (h == s && (s & 1u)) ? 1u : 0u;
   return (h << 1) | f;
@@ -400,9 +518,9 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
 // 32-vertex probe per unoriented cycle.  word(v) = label << 2 | oriented << 1 | adjacency.
 // Returns the verdict to all threads; "false" only means "not settled, run the slow path".
 // --------------------------------------------------------------------------------------------------
-template <class WordFn>
-__device__ inline bool unoriented_cycles_all_covered(int n, int S, WordFn word) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+template <class TM, class WK, class WordFn>
+__device__ inline bool unoriented_cycles_all_covered(WK &wk, int n, int S, WordFn word) {
+  const int tid = TM::tid(), nt = TM::size(), lane = tid & 31;
   int unresolved = 0;
   for (int base = tid & ~31; base <= n && !unresolved; base += nt) {
     const int k = base + lane;
@@ -435,7 +553,7 @@ __device__ inline bool unoriented_cycles_all_covered(int n, int S, WordFn word) 
       if (!hit) { unresolved = 1; break; }            // one unsettled cycle decides: stop probing
     }
   }
-  return !__syncthreads_or(unresolved);
+  return !TM::any(unresolved, wk);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -549,7 +667,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   st.c = (int)((tot >> 21) & 0x1FFFFFu);
   st.h = 0; st.f = 0;
   if ((tot & 0x1FFFFFu) != 0 &&
-      !unoriented_cycles_all_covered(n, S, [&](unsigned v) -> unsigned {
+      !unoriented_cycles_all_covered<TeamBlock>(wk, n, S, [&](unsigned v) -> unsigned {
         const uint32_t w = W[v];
         return ((w >> 17) << 2) | (w & 3u);
       })) {
@@ -564,7 +682,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
       wk.A1[a] = (uint16_t)((w0 >> 1) & 1u);
     }
     __syncthreads();
-    unsigned hf = hurdles_slow_path(wk, n);
+    unsigned hf = hurdles_slow_path<TeamBlock>(wk, n);
     st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
   }
   st.d = st.b - st.c + st.h + st.f;
@@ -583,9 +701,9 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
 #define GRSR_L_NEXT(w) ((unsigned)(((w) >> 2) & 0x7FFFFFFFull))
 #define GRSR_L_LABEL(w) ((unsigned)((w) >> 33))
 
-template <bool kKeepOrbits, class EndsFn>
+template <class TM, bool kKeepOrbits, class EndsFn>
 __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = TM::tid(), nt = TM::size(), lane = tid & 31, wid = tid >> 5;
   const int S = wk.S;
   constexpr unsigned kNone = none_of<uint32_t>();
   unsigned long long *W = (unsigned long long *)wk.W;
@@ -614,7 +732,7 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
       }
     }
   }
-  __syncthreads();
+  TM::sync();
 
   {
     const int rounds = ceil_log2(n + 1);
@@ -627,7 +745,7 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
         for (int j = 0; j < 4; j++) { int v = v0 + j * nt; w[j] = (v < S) ? W[v] : 0ull; }
 #pragma unroll
         for (int j = 0; j < 4; j++) { int v = v0 + j * nt; u[j] = (v < S) ? W[GRSR_L_NEXT(w[j])] : 0ull; }
-        GRSR_EMU_READ_BEFORE_WRITE();
+        GRSR_EMU_READ_BEFORE_WRITE_TM();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           int v = v0 + j * nt;
@@ -638,10 +756,10 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
           }
         }
       }
-      if (!__syncthreads_or((chg & 0xFFFFFFFE00000002ull) != 0ull)) break;
+      if (!TM::any((chg & 0xFFFFFFFE00000002ull) != 0ull, wk)) break;
     }
   }
-  __syncthreads();
+  TM::sync();
 
   unsigned ncyc = 0, nun = 0;
   for (int k = tid; k <= n; k += nt) {
@@ -655,13 +773,13 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
     nun += (root && !(w0 & GRSR_W_ORBIT));
   }
   unsigned long long tot =
-      blk_sum_u64(((unsigned long long)nadj << 42) | ((unsigned long long)ncyc << 21) | nun, wk.red);
+      TM::sum(((unsigned long long)nadj << 42) | ((unsigned long long)ncyc << 21) | nun, wk);
   Stats st;
   st.b = (n + 1) - (int)(tot >> 42);
   st.c = (int)((tot >> 21) & 0x1FFFFFu);
   st.h = 0; st.f = 0;
   if ((tot & 0x1FFFFFu) != 0 &&
-      !unoriented_cycles_all_covered(n, S, [&](unsigned v) -> unsigned {
+      !unoriented_cycles_all_covered<TM>(wk, n, S, [&](unsigned v) -> unsigned {
         const unsigned long long w = W[v];
         return (GRSR_L_LABEL(w) << 2) | (unsigned)(w & 3ull);
       })) {
@@ -672,8 +790,8 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
       wk.A2[a] = cy; wk.A2[a + 1] = cy;
       wk.A1[a] = (unsigned)((w0 >> 1) & 1ull);
     }
-    __syncthreads();
-    unsigned hf = hurdles_slow_path(wk, n);
+    TM::sync();
+    unsigned hf = hurdles_slow_path<TM>(wk, n);
     st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
   }
   st.d = st.b - st.c + st.h + st.f;
@@ -700,6 +818,7 @@ __device__ inline void large_work_carve(WorkT<uint32_t> &wk, unsigned char *base
   if (keep_orbits) base += sv * 4;
   wk.BLK = (uint32_t *)base;
   wk.red = red_smem;
+  wk.xch = (unsigned long long *)0; wk.epoch = 0;
 }
 
 // Ends of a gene given its signed position q = +-(p+1) in pi: a forward gene at position p owns
@@ -843,7 +962,7 @@ dist_pairs_large_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
     EndsFromRowsGlobal ends;
     ends.gamma = genomes + (long long)pairs[2 * p] * n;
     ends.sinv_pi = sinv + (long long)pairs[2 * p + 1] * n;
-    Stats st = dist_core_large<false>(wk, n, ends);
+    Stats st = dist_core_large<TeamBlock, false>(wk, n, ends);
     if (threadIdx.x == 0) {
       if (stride == 1) out[p] = st.d;
       else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }

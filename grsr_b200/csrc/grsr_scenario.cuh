@@ -46,6 +46,22 @@ __device__ inline unsigned long long blk_min_u64(unsigned long long v, unsigned 
   return v;
 }
 
+template <class WK> __device__ inline unsigned long long team_min64(TeamBlock, unsigned long long v, WK &wk) {
+  return blk_min_u64(v, wk.red);
+}
+template <class WK> __device__ inline unsigned long long team_min64(TeamCluster, unsigned long long v, WK &wk) {
+  volatile unsigned long long *x = TeamCluster::slot(wk);
+  v = blk_min_u64(v, wk.red);
+  if (threadIdx.x == 0) x[cluster_rank()] = v;
+  TeamCluster::sync();
+  unsigned long long r = TeamCluster::part(x, ~0ull);
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long y = __shfl_xor_sync(kFull, r, o);
+    r = (y < r) ? y : r;
+  }
+  return r;
+}
+
 // ends() of G0 = graph(gamma = destination, pi = current) (G/opt_scenario.c:229): the signed
 // position in the current genome of the destination's t-th gene is the inverse of rho0.
 template <class SV>
@@ -78,17 +94,20 @@ struct ScenSmall {
   typedef uint16_t vid;
   typedef int16_t sval;
   typedef WorkT<uint16_t> work;
+  typedef TeamBlock team;
   template <bool kKeep, class E>
   static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core<NT, EPT, kKeep>(wk, n, e); }
 };
 
-// Policy of the global-memory build: 32-bit ids and values.
+// Policy of the global-memory build: 32-bit ids and values; TM = one block or a whole cluster per pair.
+template <class TM>
 struct ScenLarge {
   typedef uint32_t vid;
   typedef int32_t sval;
   typedef WorkT<uint32_t> work;
+  typedef TM team;
   template <bool kKeep, class E>
-  static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core_large<kKeep>(wk, n, e); }
+  static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core_large<TM, kKeep>(wk, n, e); }
 };
 
 // The scenario of every pair this block draws from the ticket.  CUR, SDST, INV0, RHO0: n values
@@ -103,19 +122,20 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
                                      int npairs, int n, int32_t *__restrict__ steps,
                                      int32_t *__restrict__ nsteps, int max_steps,
                                      int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                                     unsigned int *ticket, int *s_pair) {
+                                     unsigned int *ticket, volatile int *s_pair, volatile unsigned *bound) {
   typedef typename Pol::sval SV;
   typedef typename Pol::vid VT;
+  typedef typename Pol::team TM;
   constexpr unsigned kNone = none_of<VT>();
   const unsigned long long kNoKey = ~0ull;
   const VT *ORB = wk.ORB;
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = TM::tid(), nt = TM::size();
 
   for (;;) {
     if (tid == 0) *s_pair = (int)atomicAdd(ticket, 1u);
-    __syncthreads();
+    TM::sync();
     const int p = *s_pair;
-    __syncthreads();
+    TM::sync();
     if (p >= npairs) break;
 
     const int32_t *ps = src + (long long)p * n, *pd = dst + (long long)p * n;
@@ -124,7 +144,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
       int g = pd[i];
       SDST[(g > 0 ? g : -g) - 1] = (SV)(g > 0 ? (i + 1) : -(i + 1));
     }
-    __syncthreads();
+    TM::sync();
 
     int ns = 0, code = GRSR_SCEN_OK;
     unsigned long long nevals = 0;
@@ -138,7 +158,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
         RHO0[i] = (SV)r;
         INV0[(r > 0 ? r : -r) - 1] = (SV)(r > 0 ? (i + 1) : -(i + 1));
       }
-      __syncthreads();
+      TM::sync();
       EndsG0<SV> eg; eg.inv0 = INV0;
       const Stats g0 = Pol::template dist<true>(wk, n, eg);   // G/opt_scenario.c:229
       if (g0.d == 0) break;
@@ -146,21 +166,20 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
 
       // black edges that are breakpoints, ascending: edge k = (2k, 2k+1) sits left of position k.
       // A reversal (i, j) cuts edges i and j+1 (the tests of G/opt_scenario.c:538-561).
-      const int nbp = blk_compact(n + 1, [&](int k, unsigned &val) -> bool {
+      const int nbp = TM::compact(n + 1, [&](int k, unsigned &val) -> bool {
         if (ORB[2 * k] == kNone) return false;
         val = (unsigned)k; return true;
-      }, BPL, wk.red);
+      }, BPL, wk);
       const bool filter = (g0.h == 0);                        // G/opt_scenario.c:951
 
       unsigned long long lastkey = kNoKey;
       int fi = -1, fj = -1;
       // smallest reversal length found so far in the current search, shared by the block: a lane
       // whose orbit partner is far away stops scanning as soon as somebody has a shorter candidate
-      volatile unsigned *bound = (volatile unsigned *)&wk.red[33];
       for (;;) {
         // smallest key (j - i, i) greater than lastkey among admissible candidates
         if (tid == 0) *bound = 0xFFFFFFFFu;
-        __syncthreads();
+        TM::sync();
         unsigned long long best = kNoKey;
         for (int t = tid; t < nbp; t += nt) {
           int e1 = (int)BPL[t];
@@ -187,10 +206,10 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
             const unsigned len0 = (unsigned)(e2 - e1 - 1);
             unsigned long long key = ((unsigned long long)len0 << 32) | (unsigned)e1;
             best = (key < best) ? key : best;
-            atomicMin((unsigned *)&wk.red[33], len0);
+            atomicMin((unsigned *)bound, len0);
           }
         }
-        best = blk_min_u64(best, wk.red);
+        best = team_min64(TM(), best, wk);
         if (best == kNoKey) break;
         const int i = (int)(best & 0xFFFFFFFFull);
         const int j = i + (int)(best >> 32);
@@ -213,13 +232,13 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
         o[0] = fi; o[1] = fj;
       }
       ns++;
-      __syncthreads();
+      TM::sync();
     }
     if (tid == 0) {
       nsteps[p] = ns; status[p] = code;
       if (evals) evals[p] = nevals;
     }
-    __syncthreads();
+    TM::sync();
   }
 }
 
@@ -243,7 +262,8 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
   uint16_t *BPL = (uint16_t *)(extra + 4 * scen_arr_bytes(n));
   __shared__ int s_pair;
   scenario_body<ScenSmall<NT, EPT> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
-                                     max_steps, status, evals, ticket, &s_pair);
+                                     max_steps, status, evals, ticket, &s_pair,
+                                     (volatile unsigned *)&wk.red[33]);
 }
 
 __host__ __device__ inline size_t scen_large_arr_bytes(int n) { return (((size_t)n + 2) * 4 + 15) & ~(size_t)15; }
@@ -268,8 +288,61 @@ scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict
   int32_t *INV0 = (int32_t *)(extra + 2 * scen_large_arr_bytes(n));
   int32_t *RHO0 = (int32_t *)(extra + 3 * scen_large_arr_bytes(n));
   uint32_t *BPL = (uint32_t *)(extra + 4 * scen_large_arr_bytes(n));
-  scenario_body<ScenLarge>(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
-                           max_steps, status, evals, ticket, &s_pair);
+  scenario_body<ScenLarge<TeamBlock> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
+                                       max_steps, status, evals, ticket, &s_pair,
+                                       (volatile unsigned *)&red[33]);
+}
+
+// cluster build: one thread-block cluster per pair, workspace scratch + cluster * scen_large_bytes(n),
+// exchange area xch_all + cluster * kXchWords (its last words hold the pair ticket and the search
+// bound).  Dynamic shared memory: 34 u64 of per-block reduction scratch.
+__global__ void __launch_bounds__(1024)
+scenario_cluster_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
+                        int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
+                        int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
+                        unsigned int *ticket, unsigned char *scratch, unsigned long long *xch_all) {
+  GRSR_DYN_SMEM(smem_raw);
+  unsigned long long *red = (unsigned long long *)smem_raw;
+  const unsigned cid = blockIdx.x / cluster_size();
+  unsigned char *base = scratch + (size_t)cid * scen_large_bytes(n);
+  unsigned long long *xch = xch_all + (size_t)cid * kXchWords;
+  WorkT<uint32_t> wk;
+  large_work_carve(wk, base, n, true, red);
+  wk.xch = xch;
+  unsigned char *extra = base + large_work_bytes(n, true);
+  int32_t *CUR = (int32_t *)extra;
+  int32_t *SDST = (int32_t *)(extra + scen_large_arr_bytes(n));
+  int32_t *INV0 = (int32_t *)(extra + 2 * scen_large_arr_bytes(n));
+  int32_t *RHO0 = (int32_t *)(extra + 3 * scen_large_arr_bytes(n));
+  uint32_t *BPL = (uint32_t *)(extra + 4 * scen_large_arr_bytes(n));
+  scenario_body<ScenLarge<TeamCluster> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
+                                         max_steps, status, evals, ticket,
+                                         (volatile int *)(xch + kXchWords - 4),
+                                         (volatile unsigned *)(xch + kXchWords - 2));
+}
+
+// cluster build of the batched distance (few, very long pairs)
+__global__ void __launch_bounds__(1024)
+dist_pairs_cluster_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                          const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
+                          int stride, unsigned char *scratch, unsigned long long *xch_all) {
+  GRSR_DYN_SMEM(smem_raw);
+  unsigned long long *red = (unsigned long long *)smem_raw;
+  const unsigned cs = cluster_size();
+  const unsigned cid = blockIdx.x / cs, nclusters = gridDim.x / cs;
+  WorkT<uint32_t> wk;
+  large_work_carve(wk, scratch + (size_t)cid * large_work_bytes(n, false), n, false, red);
+  wk.xch = xch_all + (size_t)cid * kXchWords;
+  for (long long p = cid; p < npairs; p += nclusters) {
+    EndsFromRowsGlobal ends;
+    ends.gamma = genomes + (long long)pairs[2 * p] * n;
+    ends.sinv_pi = sinv + (long long)pairs[2 * p + 1] * n;
+    Stats st = dist_core_large<TeamCluster, false>(wk, n, ends);
+    if (TeamCluster::tid() == 0) {
+      if (stride == 1) out[p] = st.d;
+      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
+    }
+  }
 }
 
 } // namespace grsr

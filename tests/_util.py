@@ -119,17 +119,22 @@ def emulator():
     return _emu
 
 
-def emu_stats(genomes, pairs, threads: int = 64, grid: int = 2, large: bool = False) -> np.ndarray:
+def emu_stats(genomes, pairs, threads: int = 64, grid: int = 2, large: bool = False,
+              cluster: int = 0) -> np.ndarray:
     g = _i32(genomes)
     pr = _i32(pairs).reshape(-1, 2)
     out = np.zeros((len(pr), 5), dtype=np.int32)
+    if cluster:
+        emulator().emu_dist_pairs_cluster(_p(g), g.shape[0], g.shape[1], _p(pr), ctypes.c_longlong(len(pr)),
+                                          _p(out), 5, threads, grid, cluster)
+        return out
     fn = emulator().emu_dist_pairs_large if large else emulator().emu_dist_pairs
     fn(_p(g), g.shape[0], g.shape[1], _p(pr), ctypes.c_longlong(len(pr)), _p(out),
                               5, threads, grid)
     return out
 
 
-def emu_scenario(srcs, dsts, threads: int = 64, grid: int = 2, large: bool = False):
+def emu_scenario(srcs, dsts, threads: int = 64, grid: int = 2, large: bool = False, cluster: int = 0):
     S = _i32(srcs)
     D = _i32(dsts)
     npairs, n = S.shape
@@ -138,9 +143,13 @@ def emu_scenario(srcs, dsts, threads: int = 64, grid: int = 2, large: bool = Fal
     ns = np.zeros(npairs, dtype=np.int32)
     st = np.zeros(npairs, dtype=np.int32)
     ev = np.zeros(npairs, dtype=np.uint64)
-    fn = emulator().emu_scenario_large if large else emulator().emu_scenario
-    fn(_p(S), _p(D), npairs, n, _p(steps), _p(ns), ms, _p(st),
-                            ev.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong)), threads, grid)
+    evp = ev.ctypes.data_as(ctypes.POINTER(ctypes.c_ulonglong))
+    if cluster:
+        emulator().emu_scenario_cluster(_p(S), _p(D), npairs, n, _p(steps), _p(ns), ms, _p(st), evp,
+                                        threads, grid, cluster)
+    else:
+        fn = emulator().emu_scenario_large if large else emulator().emu_scenario
+        fn(_p(S), _p(D), npairs, n, _p(steps), _p(ns), ms, _p(st), evp, threads, grid)
     return [steps[p, :ns[p]].copy() for p in range(npairs)], st, ev
 
 

@@ -41,12 +41,24 @@ struct Fiber {
   unsigned wait_gen = 0; bool at_block_bar = false;
   // warp barrier
   unsigned wwait_gen = 0; bool at_warp_bar = false;
+  // cluster barrier
+  unsigned cwait_gen = 0; bool at_cluster_bar = false;
+};
+
+struct Cluster {
+  int nblocks = 1;
+  int nthreads_total = 0;
+  unsigned gen = 0; int arrived = 0;
 };
 
 struct Block {
   int nthreads = 0;
   std::vector<Fiber> fibers;
-  ucontext_t sched;
+  ucontext_t sched_own;
+  ucontext_t *sched = &sched_own;   // blocks of one cluster share a scheduler context
+  Cluster *cluster = nullptr;
+  int cluster_rank = 0;
+  unsigned block_index = 0;
   int cur = -1;
   int live = 0;
   // block barrier state
@@ -67,7 +79,7 @@ inline Dim &gdim() { static Dim d; return d; }
 
 inline void yield_to_sched() {
   Block *b = cur_block();
-  swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+  swapcontext(&b->fibers[b->cur].ctx, b->sched);
 }
 
 inline void die(const char *msg) { fprintf(stderr, "cuda_emu: %s\n", msg); abort(); }
@@ -107,6 +119,23 @@ inline void warp_barrier(unsigned mask) {
     f.at_warp_bar = false;
   }
 }
+
+inline void cluster_barrier() {
+  Block *b = cur_block();
+  Cluster *c = b->cluster;
+  if (!c) die("cluster barrier outside a cluster launch");
+  Fiber &f = b->fibers[b->cur];
+  unsigned my_gen = c->gen;
+  if (++c->arrived == c->nthreads_total) {
+    c->arrived = 0; c->gen++;
+  } else {
+    f.at_cluster_bar = true; f.cwait_gen = my_gen;
+    while (c->gen == my_gen) yield_to_sched();
+    f.at_cluster_bar = false;
+  }
+}
+inline unsigned cluster_rank() { return (unsigned)cur_block()->cluster_rank; }
+inline unsigned cluster_size() { Block *b = cur_block(); return b->cluster ? (unsigned)b->cluster->nblocks : 1u; }
 
 inline unsigned char *dyn_smem() { return cur_block()->smem.data(); }
 
@@ -150,11 +179,64 @@ inline void launch(unsigned grid, unsigned block, size_t smem_bytes, const std::
         if (f.at_block_bar && blk.gen == f.wait_gen) continue;
         if (f.at_warp_bar && blk.wgen[t >> 5] == f.wwait_gen) continue;
         blk.cur = (int)t; tidx().x = t;
-        swapcontext(&blk.sched, &f.ctx);
+        swapcontext(blk.sched, &f.ctx);
         progressed = 1;
         if (f.done) remaining--;
       }
       if (!progressed) die("deadlock: every live thread waits at a barrier (divergent barrier?)");
+    }
+    cur_block() = nullptr;
+  }
+}
+
+// Run `body` as `nclusters` clusters of `cs` blocks of `block` threads; the blocks of a cluster run
+// concurrently (their fibers share one scheduler) so that cluster barriers can be emulated.
+inline void launch_clusters(unsigned nclusters, unsigned cs, unsigned block, size_t smem_bytes,
+                            const std::function<void()> &body) {
+  if (block == 0 || block > 1024 || cs == 0 || cs > 16) die("bad cluster launch");
+  gdim().x = nclusters * cs; bdim().x = block;
+  static const size_t kStack = 64 * 1024;
+  for (unsigned ci = 0; ci < nclusters; ci++) {
+    Cluster cl;
+    cl.nblocks = (int)cs; cl.nthreads_total = (int)(cs * block);
+    ucontext_t sched;
+    std::vector<Block> blks(cs);
+    for (unsigned r = 0; r < cs; r++) {
+      Block &blk = blks[r];
+      blk.nthreads = (int)block; blk.live = (int)block; blk.body = &body;
+      blk.smem.assign(smem_bytes + 16, 0xCD);
+      blk.fibers.resize(block);
+      memset(blk.wgen, 0, sizeof blk.wgen); memset(blk.warrived, 0, sizeof blk.warrived);
+      blk.sched = &sched; blk.cluster = &cl; blk.cluster_rank = (int)r; blk.block_index = ci * cs + r;
+      for (unsigned t = 0; t < block; t++) {
+        Fiber &f = blk.fibers[t];
+        f.stack.resize(kStack);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = kStack;
+        f.ctx.uc_link = nullptr;
+        makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+      }
+    }
+    int remaining = (int)(cs * block);
+    while (remaining > 0) {
+      int progressed = 0;
+      for (unsigned r = 0; r < cs; r++) {
+        Block &blk = blks[r];
+        for (unsigned t = 0; t < block; t++) {
+          Fiber &f = blk.fibers[t];
+          if (f.done) continue;
+          if (f.at_block_bar && blk.gen == f.wait_gen) continue;
+          if (f.at_warp_bar && blk.wgen[t >> 5] == f.wwait_gen) continue;
+          if (f.at_cluster_bar && cl.gen == f.cwait_gen) continue;
+          cur_block() = &blk;
+          blk.cur = (int)t; tidx().x = t; bidx().x = blk.block_index;
+          swapcontext(&sched, &f.ctx);
+          progressed = 1;
+          if (f.done) remaining--;
+        }
+      }
+      if (!progressed) die("deadlock in cluster launch (divergent barrier?)");
     }
     cur_block() = nullptr;
   }

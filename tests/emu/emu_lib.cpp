@@ -61,3 +61,35 @@ extern "C" int emu_scenario_large(const int32_t *src, const int32_t *dst, int np
   });
   return 0;
 }
+
+// the cluster build (several blocks per pair), run at small n
+extern "C" int emu_dist_pairs_cluster(const int32_t *genomes, int G, int n, const int32_t *pairs,
+                                      long long npairs, int32_t *out, int stride, int threads,
+                                      int nclusters, int cs) {
+  std::vector<int32_t> sinv((size_t)G * n);
+  long long total = (long long)G * n;
+  int32_t *sp = sinv.data();
+  emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
+  std::vector<unsigned char> scratch(grsr::large_work_bytes(n, false) * (size_t)nclusters + 64);
+  std::vector<unsigned long long> xch((size_t)grsr::kXchWords * nclusters, 0xCDCDCDCDCDCDCDCDull);
+  unsigned char *sc = scratch.data();
+  unsigned long long *xp = xch.data();
+  emu::launch_clusters((unsigned)nclusters, (unsigned)cs, (unsigned)threads, 34 * 8, [&] {
+    grsr::dist_pairs_cluster_kernel(genomes, sp, n, pairs, npairs, out, stride, sc, xp);
+  });
+  return 0;
+}
+
+extern "C" int emu_scenario_cluster(const int32_t *src, const int32_t *dst, int npairs, int n, int32_t *steps,
+                                    int32_t *nsteps, int max_steps, int32_t *status,
+                                    unsigned long long *evals, int threads, int nclusters, int cs) {
+  unsigned int ticket = 0;
+  std::vector<unsigned char> scratch(grsr::scen_large_bytes(n) * (size_t)nclusters + 64);
+  std::vector<unsigned long long> xch((size_t)grsr::kXchWords * nclusters, 0xCDCDCDCDCDCDCDCDull);
+  unsigned char *sc = scratch.data();
+  unsigned long long *xp = xch.data();
+  emu::launch_clusters((unsigned)nclusters, (unsigned)cs, (unsigned)threads, 34 * 8, [&] {
+    grsr::scenario_cluster_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, sc, xp);
+  });
+  return 0;
+}

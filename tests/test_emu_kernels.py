@@ -64,3 +64,36 @@ def test_emulated_scenarios(n):
         assert status[q] == 0
         assert np.array_equal(steps[q], want)
         assert evals[q] == want_evals      # same candidates tried in the same order
+
+
+# ---- the global-memory build (one block per pair) and its cluster variant (several blocks per pair) --
+
+@pytest.mark.parametrize("cluster", [0, 2, 3])
+def test_emulated_large_build_distances(cluster):
+    for n in (3, 17, 64, 100):
+        g = U.mixed_genomes(n, 8, seed=n)
+        pairs = _ordered(len(g))
+        got = U.emu_stats(g, pairs, 64, 2, large=True, cluster=cluster)
+        assert np.array_equal(got, U.orc_stats(g, pairs)), (n, cluster)
+    z = np.load(U.GOLDEN + "/stats_mixed.npz")
+    g = z["gfort"]
+    assert np.array_equal(U.emu_stats(g, _ordered(len(g)), 64, 2, large=True, cluster=cluster), z["sfort"])
+
+
+@pytest.mark.parametrize("cluster", [0, 2, 4])
+def test_emulated_large_build_scenarios(cluster):
+    for n in (2, 8, 21):
+        srcs, dsts = [], []
+        for s in range(8):
+            seed = n * 100 + s
+            rng = random.Random(seed)
+            if s % 2 == 0:
+                src, dst = gen.random_signed_perm(n, rng), gen.random_signed_perm(n, rng)
+            else:
+                src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
+            srcs.append(src)
+            dsts.append(dst)
+        steps, status, evals = U.emu_scenario(srcs, dsts, 32, 2, large=True, cluster=cluster)
+        for q in range(len(srcs)):
+            want, want_evals = U.orc_scenario(srcs[q], dsts[q])
+            assert status[q] == 0 and np.array_equal(steps[q], want) and evals[q] == want_evals

@@ -100,3 +100,54 @@ def test_too_many_genes_is_refused():
     with pytest.raises(capi.GrsrError):
         capi.dist_pairs(g, [[0, 0]])
     assert n > 1000000
+
+
+@pytest.fixture(params=[2, 8, 16])
+def force_cluster(request):
+    """global-memory build with one thread-block cluster of 2 / 8 / 16 blocks per pair"""
+    os.environ["GRSR_FORCE_LARGE"] = "1"
+    os.environ["GRSR_CLUSTER"] = str(request.param)
+    yield request.param
+    os.environ.pop("GRSR_FORCE_LARGE", None)
+    os.environ.pop("GRSR_CLUSTER", None)
+
+
+def test_cluster_build_distances(force_cluster):
+    for n in (5, 64, 300, 2000):
+        g = U.mixed_genomes(n, 8, seed=n + force_cluster)
+        pairs = _ordered(len(g))
+        assert np.array_equal(capi.dist_pairs(g, pairs, stats=True), U.orc_stats(g, pairs)), n
+    z = np.load(U.GOLDEN + "/stats_mixed.npz")
+    g = z["gfort"]
+    assert np.array_equal(capi.dist_pairs(g, _ordered(len(g)), stats=True), z["sfort"])
+
+
+def test_cluster_build_scenarios(force_cluster):
+    for n in (3, 40, 200):
+        srcs, dsts = [], []
+        for s in range(8):
+            seed = n * 100 + s
+            rng = random.Random(seed)
+            if s % 2 == 0:
+                src, dst = gen.random_signed_perm(n, rng), gen.random_signed_perm(n, rng)
+            else:
+                src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
+            srcs.append(src)
+            dsts.append(dst)
+        got = capi.scenario_batch(np.array(srcs, dtype=np.int32), np.array(dsts, dtype=np.int32))
+        for s, d, steps in zip(srcs, dsts, got):
+            want, _ = U.orc_scenario(s, d)
+            assert np.array_equal(steps, want), (n, force_cluster)
+
+
+def test_single_long_pair_uses_a_cluster_and_sorts():
+    """One random pair of n = 12000 (beyond the on-chip scenario kernels): the library gives it a
+    16-block cluster; the scenario has exactly d steps and sorts."""
+    n = 12000
+    rng = random.Random(8)
+    src = np.array(gen.random_signed_perm(n, rng), dtype=np.int32)
+    dst = np.arange(1, n + 1, dtype=np.int32)
+    steps = capi.scenario_batch(src, dst)[0]
+    d = capi.dist_pairs(np.stack([src, dst]), [[0, 1]])[0]
+    assert len(steps) == d and d > n - 20
+    assert np.array_equal(U.apply_steps(src, steps), dst)
