@@ -72,8 +72,8 @@ def test_forced_large_scenarios(force_large, n):
 
 def test_natural_large_distances():
     """Beyond the on-chip limit the library switches builds by itself."""
-    assert capi.max_genes_on_chip(False) < 12000 <= capi.max_genes()
-    for n, count in ((12000, 6), (40000, 3), (100000, 2)):
+    assert capi.max_genes_on_chip(False) < 16000 <= capi.max_genes()
+    for n, count in ((16000, 6), (40000, 3), (100000, 2)):
         rng = random.Random(n)
         rows = [list(range(1, n + 1))] + [gen.random_signed_perm(n, rng) for _ in range(count - 2)]
         rows.append(gen.hurdle_rich_perm(n, 7))
