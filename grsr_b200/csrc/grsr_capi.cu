@@ -333,7 +333,10 @@ int shard_pairs(const int32_t *genomes, int G, int n, PairSource src, const int3
 int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npairs, int n,
                        grsr_step_t *steps, int32_t *nsteps, int max_steps) {
   if (npairs <= 0) return GRSR_OK;
+  if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
+  // one scenario call at a time per device: the global-memory build's workspace is shared
+  std::lock_guard<std::recursive_mutex> device_lock(g_cache[dev].mu);
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;

@@ -100,7 +100,9 @@ int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int 
                         int first_device, int ngpus);
 
 /* ---- device-resident entry points (pointers are CUDA device pointers on the CURRENT device;
- *      stream is a cudaStream_t; no validation, no copies, asynchronous) ------------------------- */
+ *      stream is a cudaStream_t; no validation, no copies, asynchronous).  Beyond
+ *      grsr_max_genes_on_chip() genes the kernels use a per-device workspace the library owns:
+ *      keep at most one such call in flight per device. ------------------------------------------ */
 
 /* signed inverse of every genome: d_sinv[g*n + |x|-1] = sign(x) * (position of x in genome g + 1) */
 int grsr_signed_inverse_dev(const int32_t *d_genomes, int num_genomes, int num_genes,
