@@ -74,12 +74,12 @@ struct DevBuf {
 // Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
 // survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
 // 20 MB around it would cost as much again).  One call at a time per device (mutex).
-const int kCacheSlots = 6;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4 large-build scratch
+const int kCacheSlots = 7;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4-5 large-build scratch, 6 error word
 struct DevCache {
   std::recursive_mutex mu;
   cudaStream_t stream = nullptr;
-  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0};
+  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0, 0};
 };
 const int kMaxDevices = 64;
 DevCache g_cache[kMaxDevices];
@@ -243,7 +243,80 @@ int check_device_range(int first_device, int ngpus) {
   return GRSR_OK;
 }
 
+// check_genes of the reference (G/mcread_input.c:83-135) on the device, fused with the signed
+// inverse: pass 1 rejects zero / too-large genes and records, per gene, the first position holding
+// it; pass 2 flags every later position holding the same gene; pass 3 turns positions into signed
+// inverses.  The first offence in reading order (smallest genome, then smallest position -- the
+// reference's order) lands in *err as genome << 34 | position << 2 | kind.
+__global__ void validate_first_positions(const int32_t *__restrict__ genomes, int32_t *slot,
+                                         long long total, int n, unsigned long long *err) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long row = e / n; int pos = (int)(e - row * n);
+    long long g = genomes[e], a = g < 0 ? -g : g;
+    if (a == 0) atomicMin(err, ((unsigned long long)row << 34) | ((unsigned long long)pos << 2) | 0ull);
+    else if (a > n) atomicMin(err, ((unsigned long long)row << 34) | ((unsigned long long)pos << 2) | 1ull);
+    else atomicMin(&slot[row * n + (a - 1)], pos);
+  }
+}
+
+__global__ void validate_duplicates(const int32_t *__restrict__ genomes, const int32_t *__restrict__ slot,
+                                    long long total, int n, unsigned long long *err) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long row = e / n; int pos = (int)(e - row * n);
+    long long g = genomes[e], a = g < 0 ? -g : g;
+    if (a >= 1 && a <= n && slot[row * n + (a - 1)] != pos)
+      atomicMin(err, ((unsigned long long)row << 34) | ((unsigned long long)pos << 2) | 2ull);
+  }
+}
+
+__global__ void positions_to_signed_inverse(const int32_t *__restrict__ genomes, int32_t *slot,
+                                            long long total, int n) {
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    long long row = e / n;
+    int pos = slot[e];
+    slot[e] = genomes[row * n + pos] > 0 ? (pos + 1) : -(pos + 1);
+  }
+}
+
+// Validates the resident genome table and leaves its signed inverses in d_sinv.  One 8-byte
+// device-to-host read; on an offence the message uses the reference's wording.
+int validate_and_invert(const int32_t *genomes_host, const int32_t *d_genomes, int G, int n,
+                        int32_t *d_sinv, unsigned long long *d_err, cudaStream_t st) {
+  long long total = (long long)G * n;
+  int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  unsigned long long err = ~0ull;
+  CK(cudaMemsetAsync(d_sinv, 0x7f, (size_t)total * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(d_err, 0xff, sizeof(unsigned long long), st));
+  validate_first_positions<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n, d_err);
+  validate_duplicates<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n, d_err);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (err != ~0ull) {
+    long long row = (long long)(err >> 34);
+    int pos = (int)((err >> 2) & 0xFFFFFFFFull), kind = (int)(err & 3ull);
+    long long g = genomes_host[row * n + pos], a = g < 0 ? -g : g;
+    if (kind == 0) return fail(GRSR_ERR_INVALID, "genome %lld: input gene == 0", row + 1);
+    if (kind == 1)
+      return fail(GRSR_ERR_INVALID, "genome %lld: input gene (%lld) larger than number of genes %d",
+                  row + 1, g, n);
+    return fail(GRSR_ERR_INVALID, "genome %lld: duplicate gene (%lld)", row + 1, a);
+  }
+  positions_to_signed_inverse<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n);
+  CK(cudaGetLastError());
+  return GRSR_OK;
+}
+
 // check_genes of the reference (G/mcread_input.c:83-135): every row a signed permutation of 1..n
+// shape check only; the contents of a distance job's table are validated on the device
+int check_table(const int32_t *genomes, long long rows, int n) {
+  if (!genomes || n < 1 || rows < 1) return fail(GRSR_ERR_INVALID, "empty genome table");
+  return check_genes_fit(n);
+}
+
 int check_genomes(const int32_t *genomes, long long rows, int n) {
   if (!genomes || n < 1 || rows < 1) return fail(GRSR_ERR_INVALID, "empty genome table");
   std::vector<unsigned char> seen((size_t)n + 1);
@@ -284,8 +357,12 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
       (rc = cache_reserve(c, 2, (size_t)count * 2 * sizeof(int32_t), &dp)) ||
       (rc = cache_reserve(c, 3, (size_t)count * stride * sizeof(int32_t), &dout)))
     return rc;
+  void *derr;
+  if ((rc = cache_reserve(c, 6, sizeof(unsigned long long), &derr))) return rc;
   CK(cudaMemcpyAsync(dg, genomes, gbytes, cudaMemcpyHostToDevice, st));
-  if ((rc = grsr_signed_inverse_dev((const int32_t *)dg, G, n, (int32_t *)ds, st))) return rc;
+  if ((rc = validate_and_invert(genomes, (const int32_t *)dg, G, n, (int32_t *)ds,
+                                (unsigned long long *)derr, st)))
+    return rc;
   if (src == PAIRS_LIST) {
     CK(cudaMemcpyAsync(dp, pairs_host + 2 * first, (size_t)count * 2 * sizeof(int32_t),
                        cudaMemcpyHostToDevice, st));
@@ -506,7 +583,7 @@ int grsr_dist_pairs(const int32_t *genomes, int num_genomes, int num_genes, cons
   if (rc) return rc;
   if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
   if (npairs < 0 || (npairs > 0 && (!pairs || !out))) return fail(GRSR_ERR_INVALID, "null buffer");
-  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
   for (int64_t p = 0; p < 2 * npairs; p++)
     if (pairs[p] < 0 || pairs[p] >= num_genomes)
       return fail(GRSR_ERR_INVALID, "pair %lld names genome %d of %d", (long long)(p / 2),
@@ -522,7 +599,7 @@ int grsr_dist_matrix_shard(const int32_t *genomes, int num_genomes, int num_gene
   if (rc) return rc;
   if (num_shards < 1 || shard < 0 || shard >= num_shards || !out || !count)
     return fail(GRSR_ERR_INVALID, "bad shard %d of %d", shard, num_shards);
-  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
   long long P = (long long)num_genomes * (num_genomes - 1) / 2;
   long long lo = P * shard / num_shards, hi = P * (shard + 1) / num_shards;
   *count = hi - lo;
@@ -535,7 +612,7 @@ int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes, int
   int rc = check_device_range(first_device, ngpus);
   if (rc) return rc;
   if (!distmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
-  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
   long long G = num_genomes, P = G * (G - 1) / 2;
   std::vector<int32_t> flat((size_t)(P > 0 ? P : 1));
   if (P > 0) {
@@ -558,7 +635,7 @@ int grsr_stats_matrix(const int32_t *genomes, int num_genomes, int num_genes,
   int rc = check_device_range(first_device, ngpus);
   if (rc) return rc;
   if (!statsmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
-  if ((rc = check_genomes(genomes, num_genomes, num_genes))) return rc;
+  if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
   long long total = (long long)num_genomes * num_genomes;
   return shard_pairs(genomes, num_genomes, num_genes, PAIRS_SQUARE, nullptr, total,
                      (int32_t *)statsmatrix, 5, first_device, ngpus);
