@@ -42,6 +42,7 @@ SIGNATURES = {
     "grsr_stats_matrix": (ctypes.c_int, [I32P, ctypes.c_int, ctypes.c_int, I32P, ctypes.c_int, ctypes.c_int]),
     "grsr_scenario_batch": (ctypes.c_int, [I32P, I32P, ctypes.c_int, ctypes.c_int, I32P, I32P, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int]),
+    "grsr_trial_distances": (ctypes.c_int, [I32P, I32P, ctypes.c_int, I32P, ctypes.c_int64, I32P, ctypes.c_int]),
     "grsr_signed_inverse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
     "grsr_dist_pairs_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
@@ -159,6 +160,16 @@ def scenario_batch(src, dst, first_device: int = 0, ngpus: int = 1) -> list[np.n
     _check(lib().grsr_scenario_batch(_p(s), _p(d), npairs, n, _p(steps), _p(ns), max_steps,
                                      first_device, ngpus))
     return [steps[p, :ns[p]].copy() for p in range(npairs)]
+
+
+def trial_distances(src, dst, cands, device: int = 0) -> np.ndarray:
+    """d(trial_c, dst) for every candidate reversal (i, j) of one pair (grimm -t 1's inner loop)."""
+    s = _i32(src)
+    d = _i32(dst)
+    c = _i32(cands).reshape(-1, 2)
+    out = np.zeros(len(c), dtype=np.int32)
+    _check(lib().grsr_trial_distances(_p(s), _p(d), len(s), _p(c), len(c), _p(out), device))
+    return out
 
 
 # ---- device-resident entry points (raw CUDA device pointers, e.g. torch.Tensor.data_ptr()) --------

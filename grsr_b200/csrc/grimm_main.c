@@ -1,7 +1,7 @@
 /* grimm_main.c -- host program with GRIMM 2.01's command line for the unichromosomal path
  * (reference G/mcmain.c:195-996), calling the B200 kernels through the C ABI of include/grsr.h.
  *
- *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 2..7] [-v]
+ *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 2..7] [-t 1] [-v]
  *
  * What is kept byte for byte (GRSR's scr/reptA.sh:61-62,453-454 greps this text):
  *   input format          mcread_data, check_genes, delete_caps   G/mcread_input.c:83-554
@@ -13,9 +13,11 @@
  *                         G/mcmain.c:1009-1283
  *   error texts + exit(-1)
  * What is NOT here: every number in the report comes from libgrsr_cuda.so (grsr_dist_pairs,
- * grsr_dist_matrix, grsr_stats_matrix, grsr_scenario_batch); this file holds no distance or
- * scenario arithmetic.  Options outside the accelerated path (multichromosomal mode, -c -z -t -u -U
- * -W -T -F -X -D -M, -S 1) are refused with a message instead of being silently mis-served.
+ * grsr_dist_matrix, grsr_stats_matrix, grsr_scenario_batch, grsr_trial_distances); this file holds
+ * no distance or scenario arithmetic.  -t 1 (print_rev_stats_t1, G/testrev.c:86-230) scores every
+ * breakpoint-to-breakpoint reversal in one batched call.  Options outside the accelerated path
+ * (multichromosomal mode, -c -z -t 2..4 -u -U -W -T -F -X -D -M, -S 1) are refused with a message
+ * instead of being silently mis-served.
  */
 #include <ctype.h>
 #include <stdio.h>
@@ -53,6 +55,8 @@ static void usage(const char *prog)
   fprintf(stderr, "   -d: distance\n");
   fprintf(stderr, "   -s: display an optimal scenario\n");
   fprintf(stderr, "   -S #: same, #=2,...,7 (all equivalent for unichromosomal genomes)\n");
+  fprintf(stderr, "   -t 1: test all 1-step reversals, list the ones reducing distance by 1,\n");
+  fprintf(stderr, "       and give statistics\n");
   fprintf(stderr, "\nFormat of datafile: each entry has the form\n");
   fprintf(stderr, "   >human\n   5 -2 3 -1 $\n   >mouse\n   ...\n");
   fprintf(stderr, "Genes are separated by any whitespace; \"#\" starts a comment.\n\n");
@@ -397,7 +401,7 @@ int main(int argc, char *argv[])
   struct stat statbuf;
   FILE *input;
   int unichromosome = 0, circular = 0, verbose = 0;
-  int fn_distance = 0, fn_scenario = 0, scenario_type = 4, fn_any = 0, fn_matrix = 0;
+  int fn_distance = 0, fn_scenario = 0, scenario_type = 4, fn_any = 0, fn_matrix = 0, fn_revstats = 0;
   int gindex1 = -1, gindex2 = -1;
   char refused = 0;
   input_t in;
@@ -428,7 +432,14 @@ int main(int argc, char *argv[])
         errflg++;
       } else { gindex1--; gindex2--; }
       break;
-    case 'c': case 'z': case 't': case 'u': case 'M': case 'D': case 'T': case 'X': case 'F':
+    case 't':
+      if (sscanf(optarg, "%d", &fn_revstats) != 1 || fn_revstats < 1 || fn_revstats > 4) {
+        fprintf(stderr, "ERROR: -t #   must be between 1 and 4\n");
+        errflg++;
+      }
+      fn_any = 1;
+      break;
+    case 'c': case 'z': case 'u': case 'M': case 'D': case 'T': case 'X': case 'F':
     case 'U': case 'W':
       refused = (char)c;
       break;
@@ -497,6 +508,7 @@ int main(int argc, char *argv[])
       fprintf(stderr, "you must specify two genomes with the -g #,# option.\n");
     }
     fn_scenario = fn_distance = 0;
+    fn_revstats = 0;
     fn_any = fn_matrix = 1;
   }
   if (gindex1 == -1) { gindex1 = 0; gindex2 = 1; }
@@ -565,6 +577,11 @@ int main(int argc, char *argv[])
     const int32_t *g2 = in.genes + (size_t)gindex2 * (size_t)n;
 
     if (!fn_any) { fn_distance = 1; fn_scenario = 1; }
+    if (fn_revstats > 1) {
+      fprintf(stderr, "ERROR: -t %d is outside the path this build accelerates (only -t 1 is "
+                      "unichromosomal); use the original GRIMM\n", fn_revstats);
+      die_usage(argv[0]);
+    }
     if (fn_scenario && scenario_type == 1) {
       fprintf(stderr, "ERROR: -S 1 (the legacy scenario engine) is outside the path this build "
                       "accelerates; use -s or -S 2..7, or the original GRIMM\n");
@@ -609,6 +626,71 @@ int main(int argc, char *argv[])
       }
       free(steps); free(cur);
     }
+  }
+
+  if (!fn_matrix && fn_revstats == 1) { /* print_rev_stats_t1, G/testrev.c:86-230 */
+    const int32_t *g1 = in.genes + (size_t)gindex1 * (size_t)n;
+    const int32_t *g2 = in.genes + (size_t)gindex2 * (size_t)n;
+    /* SUCCESSOR table of the destination (G/scenario.c:137-143): succ[g + n] for g in -n..n */
+    int32_t *succ = (int32_t *)xmalloc(sizeof(int32_t) * (2 * (size_t)n + 1), "successors");
+    char *is_start = (char *)xmalloc((size_t)n, "starts"), *is_end = (char *)xmalloc((size_t)n, "ends");
+    int32_t *cands, *d2, pair[2];
+    grsr_stats_t st;
+    long ncand = 0, c = 0;
+    int num_bkpt = 0, j, rc, d;
+    int num_down1 = 0, num_same = 0, num_up1 = 0, num_error = 0, num_tillfound = 0, foundany = 0;
+    fprintf(outfile, "\n======================================================================\n\n");
+    fprintf(outfile, "Test all single step reversals:\n\n");
+    for (i = 0; i < 2 * n + 1; i++) succ[i] = 0;
+    for (i = 0; i + 1 < n; i++) { succ[g2[i] + n] = g2[i + 1]; succ[-g2[i + 1] + n] = -g2[i]; }
+    for (i = 0; i < n; i++) {
+      is_start[i] = (char)(i == 0 || succ[g1[i - 1] + n] != g1[i]);
+      is_end[i] = (char)(i == n - 1 || succ[g1[i] + n] != g1[i + 1]);
+      num_bkpt += is_start[i];
+    }
+    num_bkpt++; /* the end counts as a breakpoint for unichromosomal genomes (:127) */
+    fprintf(outfile, "Breakpoint positions (%d):", num_bkpt);
+    for (i = 0; i < n; i++) if (is_start[i]) fprintf(outfile, " %d", i);
+    fprintf(outfile, " %d", n);
+    fprintf(outfile, "\n\n");
+    for (i = 0; i < n; i++) if (is_start[i]) for (j = i; j < n; j++) if (is_end[j]) ncand++;
+    cands = (int32_t *)xmalloc(sizeof(int32_t) * 2 * (size_t)ncand, "candidates");
+    d2 = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)ncand, "trial distances");
+    for (i = 0; i < n; i++) if (is_start[i]) for (j = i; j < n; j++) if (is_end[j]) {
+      cands[2 * c] = i; cands[2 * c + 1] = j; c++;
+    }
+    pair[0] = gindex1; pair[1] = gindex2;
+    rc = grsr_dist_pairs(in.genes, G, n, pair, 1, (int32_t *)&st, 5, first_device(), 1);
+    if (rc) gpu_fail(rc);
+    d = st.d;
+    rc = grsr_trial_distances(g1, g2, n, cands, ncand, d2, first_device());
+    if (rc) gpu_fail(rc);
+    c = 0;
+    for (i = 0; i < n; i++) {
+      int foundany_i = 0;
+      if (!is_start[i]) continue;
+      for (j = i; j < n; j++) {
+        if (!is_end[j]) continue;
+        if (!foundany) num_tillfound++;
+        if (d2[c] == d - 1) {
+          num_down1++;
+          if (!foundany_i) { fprintf(outfile, "%d: ", i); foundany = foundany_i = 1; }
+          fprintf(outfile, " %d", j);
+        } else if (d2[c] == d) num_same++;
+        else if (d2[c] == d + 1) num_up1++;
+        else {
+          num_error++;
+          fprintf(outfile, "\nERROR: Potential distance caculation error;\n");
+          fprintf(outfile, " Reversal in positions %d..%d changed distance from %d to %d\n", i, j, d, d2[c]);
+        }
+        c++;
+      }
+      if (foundany_i) fprintf(outfile, "\n");
+    }
+    fprintf(outfile, "\nNumber of reversals changing distance by\n   -1 is %d;  0 is %d;  +1 is %d;  other is %d;  total: %d\n",
+            num_down1, num_same, num_up1, num_error, num_down1 + num_same + num_up1 + num_error);
+    fprintf(outfile, "First success after %d trials\n", num_tillfound);
+    free(succ); free(is_start); free(is_end); free(cands); free(d2);
   }
 
   for (i = 0; i < G; i++) free(in.names[i]);

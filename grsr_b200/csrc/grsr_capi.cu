@@ -641,6 +641,51 @@ int grsr_stats_matrix(const int32_t *genomes, int num_genomes, int num_genes,
                      (int32_t *)statsmatrix, 5, first_device, ngpus);
 }
 
+int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes, const int32_t *cands,
+                         int64_t ncand, int32_t *out, int device) {
+  int rc = check_device_range(device, 1);
+  if (rc) return rc;
+  if (ncand < 0 || (ncand > 0 && (!cands || !out))) return fail(GRSR_ERR_INVALID, "null buffer");
+  if ((rc = check_genomes(src, 1, num_genes)) || (rc = check_genomes(dst, 1, num_genes))) return rc;
+  for (int64_t c = 0; c < ncand; c++)
+    if (cands[2 * c] < 0 || cands[2 * c] > cands[2 * c + 1] || cands[2 * c + 1] >= num_genes)
+      return fail(GRSR_ERR_INVALID, "candidate %lld: bad positions %d..%d", (long long)c, cands[2 * c],
+                  cands[2 * c + 1]);
+  if (ncand == 0) return GRSR_OK;
+  const int n = num_genes;
+  Launch L;
+  grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+  L.smem = grsr::work_bytes(n, L.threads * L.ept, false) + 2 * grsr::scen_arr_bytes(n);
+  if (n > grsr::kMaxSmemGenes || 2 * n + 2 > 32767 || L.threads * L.ept < 2 * n + 2 ||
+      L.smem > 227u * 1024u)
+    return fail(GRSR_ERR_TOOLARGE, "num_genes=%d: candidate scoring keeps the graph on chip "
+                "(at most %d genes)", n, grsr_max_genes_on_chip(0));
+  if (device < 0 || device >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", device);
+  CK(cudaSetDevice(device));
+  DevCache &c = g_cache[device];
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t st = c.stream;
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::trial_batch_kernel<kNt, kEpt>, ncand, L));
+  if (rc) return rc;
+  void *dsrc, *ddst, *dc, *dout;
+  size_t gb = (size_t)n * sizeof(int32_t);
+  if ((rc = cache_reserve(c, 0, gb, &dsrc)) || (rc = cache_reserve(c, 1, gb, &ddst)) ||
+      (rc = cache_reserve(c, 2, (size_t)ncand * 2 * sizeof(int32_t), &dc)) ||
+      (rc = cache_reserve(c, 3, (size_t)ncand * sizeof(int32_t), &dout)))
+    return rc;
+  CK(cudaMemcpyAsync(dsrc, src, gb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ddst, dst, gb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dc, cands, (size_t)ncand * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
+      (const int32_t *)dsrc, (const int32_t *)ddst, n, (const int32_t *)dc, (long long)ncand,
+      (int32_t *)dout)));
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout, (size_t)ncand * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return GRSR_OK;
+}
+
 int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int num_genes,
                         grsr_step_t *steps, int32_t *nsteps, int max_steps, int first_device,
                         int ngpus) {

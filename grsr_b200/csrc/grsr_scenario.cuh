@@ -293,6 +293,40 @@ scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict
                                        (volatile unsigned *)&red[33]);
 }
 
+// All candidate reversals of ONE (source, destination) pair scored in parallel -- the inner loop
+// of print_rev_stats_t1 (reference G/testrev.c:156-215) and the evaluation step of optrev_try_op
+// (G/opt_scenario.c:974-986): out[c] = invdist_noncircular(trial_c, dest) where trial_c is the
+// source with positions cands[2c]..cands[2c+1] reversed and negated.  One block per candidate
+// (grid-stride); rho0 of the pair is rebuilt once per block in shared memory.
+template <int NT, int EPT>
+__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
+trial_batch_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
+                   const int32_t *__restrict__ cands, long long ncand, int32_t *__restrict__ out) {
+  GRSR_DYN_SMEM(smem_raw);
+  Work wk;
+  work_carve(wk, smem_raw, n, NT * EPT, false);
+  unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, false);
+  int16_t *SDST = (int16_t *)extra;
+  int16_t *RHO0 = (int16_t *)(extra + scen_arr_bytes(n));
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += NT) {
+    int g = dst[i];
+    SDST[(g > 0 ? g : -g) - 1] = (int16_t)(g > 0 ? (i + 1) : -(i + 1));
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += NT) {
+    int g = src[i];
+    int s = SDST[(g > 0 ? g : -g) - 1];
+    RHO0[i] = (int16_t)(g > 0 ? s : -s);
+  }
+  __syncthreads();
+  for (long long c = blockIdx.x; c < ncand; c += gridDim.x) {
+    EndsTrial<int16_t> et; et.rho0 = RHO0; et.i = cands[2 * c]; et.j = cands[2 * c + 1];
+    const Stats st = dist_core<NT, EPT, false>(wk, n, et);
+    if (tid == 0) out[c] = st.d;
+  }
+}
+
 // cluster build: one thread-block cluster per pair, workspace scratch + cluster * scen_large_bytes(n),
 // exchange area xch_all + cluster * kXchWords (its last words hold the pair ticket and the search
 // bound).  Dynamic shared memory: 34 u64 of per-block reduction scratch.

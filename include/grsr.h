@@ -99,6 +99,14 @@ int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int 
                         grsr_step_t *steps, int32_t *nsteps, int max_steps,
                         int first_device, int ngpus);
 
+/* Every listed candidate reversal of one pair scored at once -- the loop of print_rev_stats_t1
+ * (G/testrev.c:156-215, `grimm -t 1`) and the evaluation of optrev_try_op (G/opt_scenario.c:974-986):
+ * out[c] = invdist_noncircular(trial_c, dst) where trial_c = src with positions cands[2c] ..
+ * cands[2c+1] (0-based, inclusive) reversed and negated (copy_and_reverse_genes, G/scenario.c:475).
+ * num_genes <= grsr_max_genes_on_chip(0). */
+int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes,
+                         const int32_t *cands, int64_t ncand, int32_t *out, int device);
+
 /* ---- device-resident entry points (pointers are CUDA device pointers on the CURRENT device;
  *      stream is a cudaStream_t; no validation, no copies, asynchronous).  Beyond
  *      grsr_max_genes_on_chip() genes the kernels use a per-device workspace the library owns:

@@ -356,6 +356,19 @@ done:
   return status < 0 ? status : nsteps;
 }
 
+void orc_trial_distances(const int *src, const int *dst, int n, const int *cands, long ncand, int *out) {
+  ws_t w; long c; int k;
+  int *trial = xcalloc(n, sizeof(int));
+  ws_init(&w, n);
+  for (c = 0; c < ncand; c++) {
+    int i = cands[2 * c], j = cands[2 * c + 1];
+    for (k = 0; k < n; k++) trial[k] = src[k];
+    for (k = i; k <= j; k++) trial[k] = -src[i + j - k];        /* G/scenario.c:475-486 */
+    out[c] = distance_ws(&w, trial, dst, NULL);                 /* gamma = trial, pi = dest */
+  }
+  ws_free(&w); free(trial);
+}
+
 static void flip_range(int *a, int lo, int hi, int negate) {
   for (; lo < hi; lo++, hi--) {
     int t = a[lo];

@@ -86,6 +86,37 @@ def ref_scenario(src, dst):
     return steps[:2 * k].reshape(-1, 2).copy()
 
 
+def orc_trial_distances(src, dst, cands) -> np.ndarray:
+    s = _i32(src)
+    d = _i32(dst)
+    c = _i32(cands).reshape(-1, 2)
+    out = np.zeros(len(c), dtype=np.int32)
+    oracle().orc_trial_distances(_p(s), _p(d), len(s), _p(c), ctypes.c_long(len(c)), _p(out))
+    return out
+
+
+def breakpoint_candidates(src, dst):
+    """(i, j) pairs print_rev_stats_t1 tries (G/testrev.c:156-184): i = 0 or a breakpoint start,
+    j = n-1 or a breakpoint end, i <= j, in i-major order."""
+    n = len(src)
+    succ = {}
+    for a, b in zip(dst[:-1], dst[1:]):
+        succ[int(a)] = int(b)
+        succ[-int(b)] = -int(a)
+    starts = [i for i in range(n) if i == 0 or succ.get(int(src[i - 1])) != int(src[i])]
+    ends = [j for j in range(n) if j == n - 1 or succ.get(int(src[j])) != int(src[j + 1])]
+    return np.array([[i, j] for i in starts for j in ends if j >= i], dtype=np.int32).reshape(-1, 2)
+
+
+def emu_trial_distances(src, dst, cands, threads: int = 0, grid: int = 3) -> np.ndarray:
+    s = _i32(src)
+    d = _i32(dst)
+    c = _i32(cands).reshape(-1, 2)
+    out = np.zeros(len(c), dtype=np.int32)
+    emulator().emu_trial_distances(_p(s), _p(d), len(s), _p(c), ctypes.c_longlong(len(c)), _p(out), threads, grid)
+    return out
+
+
 def orc_circular_align(genomes) -> np.ndarray:
     g = _i32(genomes).copy()
     oracle().orc_circular_align(_p(g), g.shape[0], g.shape[1])

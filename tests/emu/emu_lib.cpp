@@ -93,3 +93,14 @@ extern "C" int emu_scenario_cluster(const int32_t *src, const int32_t *dst, int 
   });
   return 0;
 }
+
+extern "C" int emu_trial_distances(const int32_t *src, const int32_t *dst, int n, const int32_t *cands,
+                                   long long ncand, int32_t *out, int threads, int grid) {
+  int t, e;
+  grsr::pick_shape(n, threads, &t, &e);
+  size_t smem = grsr::work_bytes(n, t * e, false) + 2 * grsr::scen_arr_bytes(n);
+  GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+    grsr::trial_batch_kernel<kNt, kEpt>(src, dst, n, cands, ncand, out);
+  }));
+  return 0;
+}

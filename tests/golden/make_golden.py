@@ -97,6 +97,11 @@ CLI_CASES = [
     ("example_C_g12_m", ["-f", "{f}", "-C", "-g", "1,2", "-m"]),
     ("example_C_g14", ["-f", "{f}", "-C", "-g", "1,4"]),
     ("example_C_gbad", ["-f", "{f}", "-C", "-g", "1"]),
+    ("example_C_g13_t1", ["-f", "{f}", "-C", "-g", "1,3", "-t", "1"]),
+    ("example_C_g12_t1_d_v", ["-f", "{f}", "-C", "-g", "1,2", "-t", "1", "-d", "-v"]),
+    ("example_L_g32_t1_s", ["-f", "{f}", "-L", "-g", "3,2", "-t", "1", "-s"]),
+    ("example_C_nog_t1", ["-f", "{f}", "-C", "-t", "1"]),
+    ("example_C_t9", ["-f", "{f}", "-C", "-g", "1,2", "-t", "9"]),
     ("nofile", ["-C"]),
     ("missingfile", ["-f", "/nonexistent/x.txt", "-C"]),
 ]
@@ -165,6 +170,9 @@ def main():
         ("hurdles_L_g21", ["-f", "{hurdles}", "-L", "-g", "2,1"]),
         ("hurdles_L_g31_v", ["-f", "{hurdles}", "-L", "-g", "3,1", "-v"]),
         ("hurdles_C_g13", ["-f", "{hurdles}", "-C", "-g", "1,3"]),
+        ("hurdles_L_g21_t1", ["-f", "{hurdles}", "-L", "-g", "2,1", "-t", "1"]),
+        ("hurdles_L_g13_t1", ["-f", "{hurdles}", "-L", "-g", "1,3", "-t", "1"]),
+        ("n120_L_g23_t1", ["-f", "{n120}", "-L", "-g", "2,3", "-t", "1"]),
         ("messy_L", ["-f", "{messy}", "-L"]),
         ("messy_C_v", ["-f", "{messy}", "-C", "-v"]),
         ("messy_L_m", ["-f", "{messy}", "-L", "-m"]),

@@ -97,3 +97,14 @@ def test_emulated_large_build_scenarios(cluster):
         for q in range(len(srcs)):
             want, want_evals = U.orc_scenario(srcs[q], dsts[q])
             assert status[q] == 0 and np.array_equal(steps[q], want) and evals[q] == want_evals
+
+
+def test_emulated_trial_distances():
+    for n in (5, 17, 40):
+        for s in range(4):
+            rng = random.Random(n * 10 + s)
+            src = gen.hurdle_rich_perm(n, n * 10 + s) if s % 2 else gen.random_signed_perm(n, rng)
+            dst = list(range(1, n + 1)) if s < 2 else gen.random_signed_perm(n, rng)
+            cands = U.breakpoint_candidates(src, dst)
+            if len(cands):
+                assert np.array_equal(U.emu_trial_distances(src, dst, cands), U.orc_trial_distances(src, dst, cands))

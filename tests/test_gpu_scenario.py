@@ -92,3 +92,29 @@ def test_random_n1000_and_round_trip_n5000():
 def test_identical_genomes_have_empty_scenario():
     p = list(range(1, 41))
     assert len(capi.scenario_batch(p, p)[0]) == 0
+
+
+def test_trial_distances_t1_counts_of_the_example():
+    """`grimm -C -g 1,3 -t 1` on the shipped example: 18 breakpoint positions, 153 reversals tried,
+    12 / 54 / 87 of them change the distance by -1 / 0 / +1."""
+    g = U.orc_circular_align(U.parse_genomes(U.EXAMPLE)[1])
+    cands = U.breakpoint_candidates(g[0], g[2])
+    d2 = capi.trial_distances(g[0], g[2], cands)
+    d = capi.dist_pairs(g, [[0, 2]])[0]
+    assert len(cands) == 153
+    assert [(d2 == d - 1).sum(), (d2 == d).sum(), (d2 == d + 1).sum()] == [12, 54, 87]
+    assert np.array_equal(d2, U.orc_trial_distances(g[0], g[2], cands))
+
+
+@pytest.mark.parametrize("n", [2, 9, 40, 150, 600])
+def test_trial_distances_vs_oracle(n):
+    for s in range(4):
+        rng = random.Random(n * 10 + s)
+        src = gen.hurdle_rich_perm(n, n * 10 + s) if s % 2 else gen.random_signed_perm(n, rng)
+        dst = list(range(1, n + 1)) if s < 2 else gen.random_signed_perm(n, rng)
+        cands = U.breakpoint_candidates(src, dst)
+        if len(cands) > 4000:
+            cands = cands[:: len(cands) // 4000 + 1]
+        if len(cands) == 0:
+            continue
+        assert np.array_equal(capi.trial_distances(src, dst, cands), U.orc_trial_distances(src, dst, cands))
