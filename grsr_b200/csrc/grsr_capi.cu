@@ -4,9 +4,11 @@
 #include "../../include/grsr.h"
 #include "grsr_core.cuh"
 #include "grsr_scenario.cuh"
+#include "grsr_stepwise.cuh"
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -447,10 +449,62 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
     CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(dtick.p, 0, 4, st));
+    int resume = 0;
+    if (small && npairs <= env_int("GRSR_STEPWISE_MAX", 16)) {
+      // Few pairs: while a pair's graph has hurdles (every breakpoint pair must be evaluated, hundreds
+      // to thousands per step) spread each step's evaluations over the whole GPU; hand the
+      // hurdle-free rest of every pair to the persistent kernel below (grsr_stepwise.cuh).
+      const int cap = (2 * (n + 1) > 4096) ? 2 * (n + 1) : 4096;
+      DevBuf dstate, dcands, dd2;
+      int r;
+      if ((r = dstate.alloc(sizeof(grsr::StepState))) || (r = dcands.alloc((size_t)cap * 2 * sizeof(int32_t))) ||
+          (r = dd2.alloc((size_t)cap * sizeof(int32_t))))
+        return r;
+      Launch LT;
+      LT.threads = L.threads; LT.ept = L.ept;
+      LT.smem = grsr::work_bytes(n, L.threads * L.ept, false) + 2 * grsr::scen_arr_bytes(n);
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::trial_batch_kernel<kNt, kEpt>, cap, LT));
+      if (r) return r;
+      { Launch LPp = L;
+        GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::step_prepare_kernel<kNt, kEpt>, 1, LPp));
+        if (r) return r; }
+      std::vector<int32_t> ns0((size_t)npairs, 0);
+      const int32_t *ncand_dev = (const int32_t *)((const char *)dstate.p + offsetof(grsr::StepState, ncand));
+      for (int p = 0; p < npairs; p++) {
+        grsr::StepState hs;
+        memset(&hs, 0, sizeof hs);
+        hs.lastkey = ~0ull; hs.batch_end = ~0ull;
+        CK(cudaMemcpyAsync(dstate.p, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+        int32_t *cur_p = (int32_t *)dsrc.p + (size_t)p * n;
+        const int32_t *dst_p = (const int32_t *)ddst.p + (size_t)p * n;
+        int32_t *steps_p = (int32_t *)dsteps.p + 2 * (size_t)p * max_steps;
+        for (;;) {
+          GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::step_prepare_kernel<kNt, kEpt><<<1, L.threads, L.smem, st>>>(
+              cur_p, dst_p, n, (grsr::StepState *)dstate.p, (int32_t *)dcands.p, cap)));
+          GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<LT.grid, LT.threads, LT.smem, st>>>(
+              cur_p, dst_p, n, (const int32_t *)dcands.p, 0LL, (int32_t *)dd2.p, ncand_dev)));
+          grsr::step_select_kernel<<<1, 256, 0, st>>>(cur_p, n, (grsr::StepState *)dstate.p,
+                                                      (const int32_t *)dcands.p, (const int32_t *)dd2.p,
+                                                      steps_p, max_steps);
+          CK(cudaGetLastError());
+          CK(cudaMemcpyAsync(&hs, dstate.p, sizeof hs, cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          if (hs.d == 0 || hs.status != GRSR_SCEN_OK || hs.h == 0) break;
+        }
+        ns0[p] = hs.nsteps;
+        if (hs.status == GRSR_SCEN_OVERFLOW)
+          return fail(GRSR_ERR_INVALID, "pair %d: scenario needs more than max_steps=%d steps", p, max_steps);
+        if (hs.status == GRSR_SCEN_STUCK)
+          return fail(GRSR_ERR_SEARCH, "pair %d: reversals ended prematurely after %d steps", p, hs.nsteps);
+      }
+      CK(cudaMemcpyAsync(dns.p, ns0.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));      // ns0 leaves scope
+      resume = 1;
+    }
     if (small) {
       GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
           (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
-          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p)));
+          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p, resume)));
     } else if (LP.cs == 1) {
       grsr::scenario_large_kernel<<<LP.grid, 1024, 0, st>>>(
           (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
@@ -679,7 +733,7 @@ int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes, 
   CK(cudaMemcpyAsync(dc, cands, (size_t)ncand * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
       (const int32_t *)dsrc, (const int32_t *)ddst, n, (const int32_t *)dc, (long long)ncand,
-      (int32_t *)dout)));
+      (int32_t *)dout, (const int32_t *)nullptr)));
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dout, (size_t)ncand * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));

@@ -122,7 +122,8 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
                                      int npairs, int n, int32_t *__restrict__ steps,
                                      int32_t *__restrict__ nsteps, int max_steps,
                                      int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                                     unsigned int *ticket, volatile int *s_pair, volatile unsigned *bound) {
+                                     unsigned int *ticket, volatile int *s_pair, volatile unsigned *bound,
+                                     int resume = 0) {
   typedef typename Pol::sval SV;
   typedef typename Pol::vid VT;
   typedef typename Pol::team TM;
@@ -146,7 +147,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
     }
     TM::sync();
 
-    int ns = 0, code = GRSR_SCEN_OK;
+    int ns = resume ? nsteps[p] : 0, code = GRSR_SCEN_OK;   // resume: steps [0, nsteps[p]) already written
     unsigned long long nevals = 0;
     for (;;) {
       // rho0 (signed position in the destination of the gene at position i of the current genome)
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
 scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                 int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                 int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                unsigned int *ticket) {
+                unsigned int *ticket, int resume) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, true);
@@ -263,7 +264,7 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
   __shared__ int s_pair;
   scenario_body<ScenSmall<NT, EPT> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
                                      max_steps, status, evals, ticket, &s_pair,
-                                     (volatile unsigned *)&wk.red[33]);
+                                     (volatile unsigned *)&wk.red[33], resume);
 }
 
 __host__ __device__ inline size_t scen_large_arr_bytes(int n) { return (((size_t)n + 2) * 4 + 15) & ~(size_t)15; }
@@ -301,7 +302,8 @@ scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict
 template <int NT, int EPT>
 __global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
 trial_batch_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int n,
-                   const int32_t *__restrict__ cands, long long ncand, int32_t *__restrict__ out) {
+                   const int32_t *__restrict__ cands, long long ncand, int32_t *__restrict__ out,
+                   const int32_t *__restrict__ ncand_dev) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, false);
@@ -309,6 +311,8 @@ trial_batch_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ 
   int16_t *SDST = (int16_t *)extra;
   int16_t *RHO0 = (int16_t *)(extra + scen_arr_bytes(n));
   const int tid = threadIdx.x;
+  if (ncand_dev) ncand = *ncand_dev;            // candidate count produced on the device
+  if ((long long)blockIdx.x >= ncand) return;
   for (int i = tid; i < n; i += NT) {
     int g = dst[i];
     SDST[(g > 0 ? g : -g) - 1] = (int16_t)(g > 0 ? (i + 1) : -(i + 1));

@@ -184,6 +184,21 @@ def emu_scenario(srcs, dsts, threads: int = 64, grid: int = 2, large: bool = Fal
     return [steps[p, :ns[p]].copy() for p in range(npairs)], st, ev
 
 
+def emu_scenario_stepwise(srcs, dsts, threads: int = 0, cap: int = 0):
+    S = _i32(srcs)
+    D = _i32(dsts)
+    npairs, n = S.shape
+    ms = n + 1
+    cap = cap or max(64, 2 * (n + 1))
+    steps = np.zeros((npairs, ms, 2), dtype=np.int32)
+    ns = np.zeros(npairs, dtype=np.int32)
+    st = np.zeros(npairs, dtype=np.int32)
+    sw = ctypes.c_int(0)
+    emulator().emu_scenario_stepwise(_p(S), _p(D), npairs, n, _p(steps), _p(ns), ms, _p(st), threads, cap,
+                                     ctypes.byref(sw))
+    return [steps[p, :ns[p]].copy() for p in range(npairs)], st, sw.value
+
+
 def mixed_genomes(n: int, count: int, seed: int) -> np.ndarray:
     """identity + a seeded mix of random, few-reversal and hurdle/fortress-rich genomes."""
     import random

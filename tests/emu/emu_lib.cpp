@@ -5,6 +5,7 @@
 #include "cuda_emu.hpp"
 #include "../../grsr_b200/csrc/grsr_core.cuh"
 #include "../../grsr_b200/csrc/grsr_scenario.cuh"
+#include "../../grsr_b200/csrc/grsr_stepwise.cuh"
 #include <vector>
 
 extern "C" int emu_dist_pairs(const int32_t *genomes, int G, int n, const int32_t *pairs,
@@ -30,7 +31,7 @@ extern "C" int emu_scenario(const int32_t *src, const int32_t *dst, int npairs, 
   grsr::pick_shape(n, threads, &t, &e);
   size_t smem = grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n);
   GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
-    grsr::scenario_kernel<kNt, kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket);
+    grsr::scenario_kernel<kNt, kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, 0);
   }));
   return 0;
 }
@@ -100,7 +101,55 @@ extern "C" int emu_trial_distances(const int32_t *src, const int32_t *dst, int n
   grsr::pick_shape(n, threads, &t, &e);
   size_t smem = grsr::work_bytes(n, t * e, false) + 2 * grsr::scen_arr_bytes(n);
   GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
-    grsr::trial_batch_kernel<kNt, kEpt>(src, dst, n, cands, ncand, out);
+    grsr::trial_batch_kernel<kNt, kEpt>(src, dst, n, cands, ncand, out, (const int32_t *)nullptr);
   }));
+  return 0;
+}
+
+// candidate-parallel steps while hurdles exist, then the persistent kernel for the rest -- the same
+// host loop as scenario_on_device() in grsr_capi.cu, with every launch going through the emulator
+extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int npairs, int n,
+                                     int32_t *steps, int32_t *nsteps, int max_steps, int32_t *status,
+                                     int threads, int cap, int *stepwise_steps) {
+  int t, e;
+  grsr::pick_shape(n, threads, &t, &e);
+  size_t smem_prep = grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n);
+  size_t smem_trial = grsr::work_bytes(n, t * e, false) + 2 * grsr::scen_arr_bytes(n);
+  std::vector<int32_t> cur((size_t)npairs * n), cands((size_t)cap * 2), d2((size_t)cap);
+  memcpy(cur.data(), src, sizeof(int32_t) * (size_t)npairs * n);
+  *stepwise_steps = 0;
+  for (int p = 0; p < npairs; p++) {
+    grsr::StepState st;
+    memset(&st, 0, sizeof st);
+    st.lastkey = ~0ull;
+    int32_t *cp = cur.data() + (size_t)p * n;
+    const int32_t *dp = dst + (size_t)p * n;
+    int32_t *sp = steps + 2 * (size_t)p * max_steps;
+    for (;;) {
+      grsr::StepState *stp = &st;
+      int32_t *cd = cands.data(), *dd = d2.data();
+      GRSR_DISPATCH_SHAPE(t, e, emu::launch(1, (unsigned)t, smem_prep, [&] {
+        grsr::step_prepare_kernel<kNt, kEpt>(cp, dp, n, stp, cd, cap);
+      }));
+      GRSR_DISPATCH_SHAPE(t, e, emu::launch(3, (unsigned)t, smem_trial, [&] {
+        grsr::trial_batch_kernel<kNt, kEpt>(cp, dp, n, cd, 0, dd, &stp->ncand);
+      }));
+      emu::launch(1, 64, 0, [&] { grsr::step_select_kernel(cp, n, stp, cd, dd, sp, max_steps); });
+      if (st.d == 0 || st.status != 0) break;
+      if (st.h == 0) break;                      // hurdle-free from here on: persistent kernel
+    }
+    nsteps[p] = st.nsteps; status[p] = st.status;
+    *stepwise_steps += st.nsteps;
+  }
+  unsigned int ticket = 0;
+  size_t smem = smem_prep;
+  const int32_t *cs = cur.data();
+  std::vector<int32_t> st2((size_t)npairs, 0);
+  int32_t *st2p = st2.data();
+  GRSR_DISPATCH_SHAPE(t, e, emu::launch(2, (unsigned)t, smem, [&] {
+    grsr::scenario_kernel<kNt, kEpt>(cs, dst, npairs, n, steps, nsteps, max_steps, st2p,
+                                     (unsigned long long *)nullptr, &ticket, 1);
+  }));
+  for (int p = 0; p < npairs; p++) if (status[p] == 0) status[p] = st2[p];
   return 0;
 }

@@ -108,3 +108,26 @@ def test_emulated_trial_distances():
             cands = U.breakpoint_candidates(src, dst)
             if len(cands):
                 assert np.array_equal(U.emu_trial_distances(src, dst, cands), U.orc_trial_distances(src, dst, cands))
+
+
+def test_emulated_stepwise_scenarios():
+    """Candidate-parallel steps while hurdles exist (prepare / score / select kernels driven by the
+    same host loop as the C ABI), then the persistent kernel: the reference's step lists, also when
+    the candidate buffer is small enough to force several batches per step."""
+    for n in (2, 5, 13, 29):
+        srcs, dsts = [], []
+        for s in range(8):
+            seed = n * 100 + s
+            rng = random.Random(seed)
+            if s % 2 == 0:
+                src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
+            else:
+                src, dst = gen.random_signed_perm(n, rng), gen.hurdle_rich_perm(n, seed)
+            srcs.append(src)
+            dsts.append(dst)
+        for cap in (0, 2 * (n + 1)):
+            steps, status, stepwise_steps = U.emu_scenario_stepwise(srcs, dsts, 0, cap)
+            for q in range(len(srcs)):
+                want, _ = U.orc_scenario(srcs[q], dsts[q])
+                assert status[q] == 0 and np.array_equal(steps[q], want)
+            assert n < 5 or stepwise_steps > 0

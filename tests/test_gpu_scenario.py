@@ -118,3 +118,22 @@ def test_trial_distances_vs_oracle(n):
         if len(cands) == 0:
             continue
         assert np.array_equal(capi.trial_distances(src, dst, cands), U.orc_trial_distances(src, dst, cands))
+
+
+def test_stepwise_and_persistent_paths_agree():
+    """With few pairs the library scores the candidates of a hurdle step across the whole GPU
+    (grsr_stepwise.cuh); with GRSR_STEPWISE_MAX=0 everything runs in the persistent kernel.  Both
+    must give the reference's step lists."""
+    import os
+    n = 120
+    srcs = np.array([gen.hurdle_rich_perm(n, 700 + s) for s in range(6)], dtype=np.int32)
+    dsts = np.tile(np.arange(1, n + 1, dtype=np.int32), (6, 1))
+    a = capi.scenario_batch(srcs, dsts)
+    os.environ["GRSR_STEPWISE_MAX"] = "0"
+    try:
+        b = capi.scenario_batch(srcs, dsts)
+    finally:
+        os.environ.pop("GRSR_STEPWISE_MAX", None)
+    for q in range(6):
+        want, _ = U.orc_scenario(srcs[q], dsts[q])
+        assert np.array_equal(a[q], want) and np.array_equal(b[q], want)
