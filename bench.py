@@ -402,6 +402,26 @@ def scenario_leg(capi):
                                "sample": "first %d pairs, one process per pair on %d cores, %.1f s; step lists equal"
                                          % (m, cores, rdt)}
     out["hurdle_rich_n300"] = leg
+    # one hurdle-rich pair alone (the command-line case): the library scores each step's candidates
+    # across the whole GPU (grsr_stepwise.cuh) instead of one after another inside one block
+    n = 300
+    one_src = np.array(gen.hurdle_rich_perm(n, 1), dtype=np.int32)
+    one_dst = np.arange(1, n + 1, dtype=np.int32)
+    capi.scenario_batch(one_src, one_dst)
+    t0 = time.perf_counter()
+    one = capi.scenario_batch(one_src, one_dst)[0]
+    dt = time.perf_counter() - t0
+    leg = {"pairs": 1, "genes": n, "reversals": len(one), "seconds": dt, "value": len(one) / dt,
+           "unit": "reversals/s"}
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")):
+        t0 = time.perf_counter()
+        ref1 = _ref_scenario_worker((one_src, one_dst))
+        rdt = time.perf_counter() - t0
+        if not np.array_equal(ref1, one):
+            raise SystemExit("GPU scenario differs from the CPU reference on the single-pair sample")
+        leg["cpu_baseline"] = {"value": len(ref1) / rdt, "unit": "reversals/s", "cores": 1, "kind": "reference",
+                               "sample": "the same pair, one process, %.2f s; step lists equal" % rdt}
+    out["single_hurdle_rich_pair_n300"] = leg
     return out
 
 
