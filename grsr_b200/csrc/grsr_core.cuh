@@ -62,7 +62,6 @@ static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex 
 //                                    are the byte offset of W[next],
 //                            [1]     1 if an oriented grey edge was seen on that window,
 //                            [0]     1 if v is an end of an adjacency (then sigma(v) = v).
-#define GRSR_W_LABEL(w) ((w) >> 17)
 #define GRSR_W_NEXT(w) (((w) >> 2) & 0x7FFFu)
 #define GRSR_W_ORBIT 2u
 #define GRSR_W_ADJ 1u
@@ -557,9 +556,9 @@ __device__ inline bool unoriented_cycles_all_covered(WK &wk, int n, int S, WordF
 }
 
 // --------------------------------------------------------------------------------------------------
-// dist_core: full invdist_noncircular_G for the pair described by inv, where
-//   inv(t) in +-(1..n), t in [0, n) = signed position in pi of the t-th gene of gamma
-// (sign = relative orientation).  Vertices are the doubled positions of pi, 0..2n+1, exactly the
+// dist_core: full invdist_noncircular_G for the pair (gamma, pi) described by ends(), which tells
+// where the two ends of gamma's t-th gene sit in pi.  Vertices are the doubled positions of pi,
+// 0..2n+1, exactly the
 // reference's numbering: gene at position p owns vertices 2p+1 (left end) and 2p+2 (right end) when
 // it reads forward, swapped when it reads backward; black edges join (2k, 2k+1).  Grey edge t
 // (t = 0..n) joins the right end of gamma's gene t-1 (vertex 0 for t = 0) to the left end of
