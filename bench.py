@@ -422,6 +422,44 @@ def scenario_leg(capi):
         leg["cpu_baseline"] = {"value": len(ref1) / rdt, "unit": "reversals/s", "cores": 1, "kind": "reference",
                                "sample": "the same pair, one process, %.2f s; step lists equal" % rdt}
     out["single_hurdle_rich_pair_n300"] = leg
+    # config-4 size: the unit of work of a hurdle-rich scenario is one full distance evaluation of
+    # a trial permutation (the reference makes ~1e7 of them per pair at n = 5000); score 16384
+    # candidate reversals of one hurdle-rich pair in one call and compare a sample with the reference
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    n = 5000
+    src5 = np.array(gen.hurdle_rich_perm(n, 4), dtype=np.int32)
+    dst5 = np.arange(1, n + 1, dtype=np.int32)
+    rng = np.random.default_rng(4)
+    ci = rng.integers(0, n, size=16384)
+    cj = rng.integers(0, n, size=16384)
+    cands = np.stack([np.minimum(ci, cj), np.maximum(ci, cj)], axis=1).astype(np.int32)
+    capi.trial_distances(src5, dst5, cands[:64])
+    t0 = time.perf_counter()
+    d2 = capi.trial_distances(src5, dst5, cands)
+    dt = time.perf_counter() - t0
+    leg = {"candidates": len(cands), "genes": n, "seconds": dt, "value": len(cands) / dt,
+           "unit": "evaluations/s", "roofline_frac_hbm": len(cands) / dt * 8 * n / 6554.6e9}
+    ref = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")
+    if os.path.exists(ref):
+        lib = ctypes.CDLL(ref)
+        cores = os.cpu_count() or 1
+        m = 64 * cores
+        trials = np.tile(src5, (m, 1))
+        for q in range(m):
+            i, j = cands[q]
+            trials[q, i:j + 1] = -src5[i:j + 1][::-1]
+        table = np.ascontiguousarray(np.vstack([trials, dst5[None, :]]), dtype=np.int32)
+        prs = np.stack([np.arange(m), np.full(m, m)], axis=1).astype(np.int32)   # gamma = trial, pi = dest
+        outr = np.zeros(m, dtype=np.int32)
+        t0 = time.perf_counter()
+        lib.ref_dist_pairs(table.ctypes.data_as(I32P), n, prs.ctypes.data_as(I32P), ctypes.c_long(m),
+                           outr.ctypes.data_as(I32P), 1, cores)
+        rdt = time.perf_counter() - t0
+        if not np.array_equal(outr, d2[:m]):
+            raise SystemExit("GPU trial distances differ from the CPU reference")
+        leg["cpu_baseline"] = {"value": m / rdt, "unit": "evaluations/s", "cores": cores, "kind": "reference",
+                               "sample": "first %d candidates on %d host threads, %.3f s; distances equal" % (m, cores, rdt)}
+    out["trial_evaluations_n5000"] = leg
     return out
 
 
