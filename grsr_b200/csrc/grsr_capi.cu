@@ -425,9 +425,15 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
   L.threads = 1024; L.ept = 0; L.smem = 0; L.grid = 1;
   LargePlan LP = {1, 1, 1, nullptr, nullptr};
   if (small) {
-    grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    // latency shape (more threads per pair) when every pair of the call is resident at once
+    grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept, 8);
     L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
+    if (!rc && L.grid < npairs) {            // more pairs than resident blocks: throughput shape
+      grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+      L.smem = grsr::work_bytes(n, L.threads * L.ept, true) + grsr::scen_extra_bytes(n);
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::scenario_kernel<kNt, kEpt>, npairs, L));
+    }
   } else {
     rc = plan_large(grsr::scenario_large_kernel, grsr::scenario_cluster_kernel, npairs,
                     grsr::scen_large_bytes(n), dev, LP);
@@ -604,9 +610,14 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   if (rc) return rc;
   if (small_fits(num_genes, false)) {
     Launch L;
-    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept, 8);
     L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
+    if (!rc && L.grid < npairs) {            // more pairs than resident blocks: throughput shape
+      grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+      L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
+    }
     if (rc) return rc;
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
         d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));

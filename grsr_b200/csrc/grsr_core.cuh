@@ -860,21 +860,29 @@ __host__ __device__ inline size_t stage_bytes(int n) { return (((size_t)n * 2) +
 
 // Launch shape of the one-pair-per-block kernels: threads per block (NT) and jumping words per
 // thread (EPT) with NT * EPT >= 2n+2, both compile-time in the kernels.  About 16 words per thread
-// keeps the per-round loop in registers while several blocks stay resident per SM.  Only the
-// combinations listed in GRSR_DISPATCH_SHAPE exist.
+// keeps the per-round loop in registers while several blocks stay resident per SM -- the shape for
+// throughput (many more pairs than resident blocks).  When all pairs of a call are resident at
+// once the pair count is the only parallelism and latency per pair matters: then 8 words per
+// thread (twice the threads per pair) is faster (target_ept = 8).  Only the combinations listed in
+// GRSR_DISPATCH_SHAPE exist.
 __host__ inline bool shape_exists(int t, int e) {
   if (t == 32) return e == 1 || e == 2 || e == 4 || e == 8 || e == 16;
-  if (t == 64) return e == 16;
+  if (t == 64) return e == 8 || e == 16;
   if (t == 128 || t == 256) return e == 8 || e == 16 || e == 32;
   if (t == 512) return e == 8 || e == 16 || e == 32 || e == 64;
   return false;
 }
 
-__host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ept) {
+__host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ept, int target_ept = 16) {
   const int S = 2 * n + 2;
   int t = 32, e = 1;
-  while (t < 512 && t * 16 < S) t *= 2;
+  while (t < 512 && t * target_ept < S) t *= 2;
   while (e < 64 && t * e < S) e *= 2;
+  if (!shape_exists(t, e)) {                 // e.g. (64, 4): fall back to the throughput shape
+    t = 32; e = 1;
+    while (t < 512 && t * 16 < S) t *= 2;
+    while (e < 64 && t * e < S) e *= 2;
+  }
   if (forced_threads > 0) {
     int fe = 1;
     while (fe < 64 && forced_threads * fe < S) fe *= 2;
@@ -890,7 +898,8 @@ __host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ep
     const int nt_ = (threads), ept_ = (ept);                                          \
     GRSR_SHAPE_CASE(32, 1, __VA_ARGS__) GRSR_SHAPE_CASE(32, 2, __VA_ARGS__)           \
     GRSR_SHAPE_CASE(32, 4, __VA_ARGS__) GRSR_SHAPE_CASE(32, 8, __VA_ARGS__)           \
-    GRSR_SHAPE_CASE(32, 16, __VA_ARGS__) GRSR_SHAPE_CASE(64, 16, __VA_ARGS__)         \
+    GRSR_SHAPE_CASE(32, 16, __VA_ARGS__) GRSR_SHAPE_CASE(64, 8, __VA_ARGS__)          \
+    GRSR_SHAPE_CASE(64, 16, __VA_ARGS__)                                              \
     GRSR_SHAPE_CASE(128, 8, __VA_ARGS__) GRSR_SHAPE_CASE(128, 16, __VA_ARGS__)        \
     GRSR_SHAPE_CASE(128, 32, __VA_ARGS__) GRSR_SHAPE_CASE(256, 8, __VA_ARGS__)        \
     GRSR_SHAPE_CASE(256, 16, __VA_ARGS__) GRSR_SHAPE_CASE(256, 32, __VA_ARGS__)       \
