@@ -5,6 +5,7 @@
 #include "grsr_core.cuh"
 #include "grsr_scenario.cuh"
 #include "grsr_stepwise.cuh"
+#include "grsr_walk.cuh"
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -76,12 +77,13 @@ struct DevBuf {
 // Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
 // survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
 // 20 MB around it would cost as much again).  One call at a time per device (mutex).
-const int kCacheSlots = 7;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4-5 large-build scratch, 6 error word
+const int kCacheSlots = 8;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4-5 large-build scratch, 6 error word,
+                             // 7 deferred-pair list of the two-tier distance path
 struct DevCache {
   std::recursive_mutex mu;
   cudaStream_t stream = nullptr;
-  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0, 0};
+  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 const int kMaxDevices = 64;
 DevCache g_cache[kMaxDevices];
@@ -126,6 +128,46 @@ int finish_plan(K kernel, long long units, Launch &L) {
   if (g > units) g = units;
   if (g < 1) g = 1;
   L.grid = (int)g;
+  return GRSR_OK;
+}
+
+// Plan of the warp-per-pair first tier (grsr_walk.cuh): warps per block chosen so that the most
+// warps stay resident per SM; grid = whole resident waves.
+struct WalkPlan { int shift; int wpb; int grid; size_t smem; int warps_per_sm; };
+
+int plan_walk(int n, long long npairs, WalkPlan &P) {
+  int dev;
+  CK(cudaGetDevice(&dev));
+  DevInfo di;
+  int rc = dev_info(dev, di);
+  if (rc) return rc;
+  auto kernel = grsr::dist_walk_kernel;
+  const size_t wb = grsr::walk_warp_bytes(n);
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          (int)cudaSharedmemCarveoutMaxShared));
+  int best_wpb = 0, best_occ = 0;
+  const int forced = env_int("GRSR_WALK_WPB", 0);
+  for (int wpb = 8; wpb >= 1; wpb >>= 1) {
+    if (forced && wpb != forced) continue;
+    const size_t smem = wb * wpb;
+    if (smem > (size_t)di.smem_optin) continue;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, wpb * 32, smem));
+    if (occ * wpb > best_occ * best_wpb) { best_wpb = wpb; best_occ = occ; }
+  }
+  if (!best_wpb) return fail(GRSR_ERR_TOOLARGE, "walk kernel does not fit on an SM (n=%d)", n);
+  int cap = env_int("GRSR_WALK_OCC", best_occ);
+  if (cap >= 1 && cap < best_occ) best_occ = cap;
+  P.shift = grsr::walk_shift(n);
+  int fs = env_int("GRSR_WALK_SHIFT", 0);
+  if (fs >= P.shift && fs <= 10) P.shift = fs;
+  P.wpb = best_wpb; P.smem = wb * best_wpb; P.warps_per_sm = best_wpb * best_occ;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+  long long g = (long long)di.sms * best_occ, need = (npairs + best_wpb - 1) / best_wpb;
+  if (g > need) g = need;
+  if (g < 1) g = 1;
+  P.grid = (int)g;
   return GRSR_OK;
 }
 
@@ -608,7 +650,37 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
   int rc = check_genes_fit(num_genes);
   if (rc) return rc;
-  if (small_fits(num_genes, false)) {
+  int dev0;
+  CK(cudaGetDevice(&dev0));
+  DevInfo di0;
+  if ((rc = dev_info(dev0, di0))) return rc;
+  // Two tiers when there are enough pairs to fill the chip with one warp per pair: the walk kernel
+  // settles every pair without hurdle candidates, the block-per-pair kernel takes the deferred rest.
+  const int walk_mode = env_int("GRSR_WALK", -1);
+  if (small_fits(num_genes, false) && walk_mode != 0 && (walk_mode == 1 || npairs >= di0.sms) &&
+      dev0 < kMaxDevices && npairs < (1ll << 31)) {
+    WalkPlan WP;
+    if ((rc = plan_walk(num_genes, npairs, WP))) return rc;
+    Launch L;
+    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_deferred_kernel<kNt, kEpt>, npairs, L));
+    if (rc) return rc;
+    void *dq;
+    {
+      DevCache &c = g_cache[dev0];
+      std::lock_guard<std::recursive_mutex> lk(c.mu);
+      if ((rc = cache_reserve(c, 7, 256 + (size_t)npairs * sizeof(int32_t), &dq))) return rc;
+    }
+    unsigned *dcount = (unsigned *)dq;
+    int32_t *dlist = (int32_t *)((char *)dq + 256);
+    CK(cudaMemsetAsync(dcount, 0, sizeof(unsigned), (cudaStream_t)stream));
+    grsr::dist_walk_kernel<<<WP.grid, WP.wpb * 32, WP.smem, (cudaStream_t)stream>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WP.shift, dlist, dcount);
+    CK(cudaGetLastError());
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_deferred_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, dlist, dcount, d_out, stride)));
+  } else if (small_fits(num_genes, false)) {
     Launch L;
     grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept, 8);
     L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);

@@ -1,0 +1,450 @@
+// grsr_walk.cuh -- warp-per-pair reversal distance: the first tier of the batched distance path.
+//
+// dist_core (grsr_core.cuh) labels the cycles of the breakpoint graph by pointer jumping over all
+// 2n+2 vertices: O(n log n) work per pair.  Here ONE WARP owns a pair and does O(n) work:
+//
+//   phase A  the same grey-edge construction as dist_core (reference double_perms + buildG_grey,
+//            G/graph_edit.c:46-157, G/mcrdist.c:116-145; adjacencies counted for num_breakpoints,
+//            G/uniinvdist.c:124-142), but stored as a 16-bit successor table
+//              H[u+1] = tau(u) = grey[u] ^ 1      ("follow the grey edge, cross the black edge")
+//            so that the two entries of a gene's two ends share one 32-bit word: one store per gene.
+//            Each lane owns 8 consecutive genes of a 256-gene chunk (two 16-byte loads), so the
+//            neighbouring genes' ends are in its own registers.  An alternating cycle of the graph is
+//            two tau-orbits (one per direction); the orbit of its leftmost vertex q (always even) has
+//            label q, the other one label q+1.
+//   walks    every vertex that is a multiple of the node stride (2^shift) is a NODE; lane l may start
+//            walks at nodes l, l+32, ...  A walk CLAIMS its start (bit 15 of the H entry), then
+//            follows tau, claiming every vertex it reaches, until it arrives at a claimed vertex --
+//            which is always the start of a walk (tau is a bijection: a segment can only be entered
+//            through its first vertex).  It leaves one word: smallest vertex of the segment, id of
+//            the walk it ran into, "an oriented grey edge was crossed".  A lane whose walk ended takes
+//            the next unclaimed node of its list, which splits whatever long stretch that node lies
+//            on: the load balances itself.  Starts happen in a separate section of the loop, so a
+//            claim is never raced.  This replaces the sequential walk of classify_cycle_path
+//            (G/graph_edit.c:207-457) with ~1.4 * 2n/32 steps per lane and ~100 walks per pair.
+//   jumping  pointer jumping over the walk words only (registers, like dist_core's phase B); the
+//            walk whose own segment holds the orbit minimum is the orbit's root.
+//   rest     vertices never claimed lie on orbits without a node (short cycles): each walks its orbit
+//            until it meets a smaller vertex; the one that gets round is the root.
+//   result   c = number of roots with an even label; when no root is unoriented every component is
+//            oriented and d = b - c (the early exit of G/graph_components.c:522-527).  Unoriented
+//            cycles first get the cheap "covered by an oriented cycle" test of dist_core; a pair it
+//            does not settle (hurdles possible), or whose leftover orbits are long, is DEFERRED: its
+//            index is appended to a list that the block-per-pair kernel (dist_deferred_kernel, the
+//            second tier, with the full component / hurdle / fortress analysis) processes next.
+//
+// Results are those of dist_core, bit for bit; only which tier computes them differs.
+#pragma once
+#include "grsr_core.cuh"
+
+#ifdef GRSR_EMU
+#define GRSR_EMU_READ_BEFORE_WRITE_WARP() __syncwarp()
+#else
+#define GRSR_EMU_READ_BEFORE_WRITE_WARP() ((void)0)
+#endif
+
+namespace grsr {
+
+static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a walk (or an adjacency end)
+static const int kWalkMaxNodes = 512;        // nodes (possible walk starts) per pair
+static const int kWalkMaxWalks = 256;        // walks per pair (8 words per lane in the jumping phase)
+static const int kWalkGroup = 4;             // tau steps between two votes
+static const int kWalkIdle = 8;              // lanes that must be out of work before new walks start
+static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
+static const int kWalkLeftoverBudget = 1536; // steps a lane may spend on orbits without a node
+
+// Node stride 2^shift for n genes: the finest one with at most kWalkMaxNodes nodes.
+__host__ __device__ inline int walk_shift(int n) {
+  const int S = 2 * n + 2;
+  int sh = 1;
+  while (((S + (1 << sh) - 1) >> sh) > kWalkMaxNodes) sh++;
+  return sh;
+}
+
+__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 3) & ~3; }   // 32-bit words of H
+
+// shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[256] | MAP u16[512] | misc
+__host__ __device__ inline size_t walk_tail_bytes(int n) { return (((size_t)(n + 1) * 2) + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t walk_warp_bytes(int n) {
+  size_t b = walk_tail_bytes(n);
+  b += (size_t)walk_hwords(n) * 4;
+  b += (size_t)kWalkMaxWalks * 4;
+  b += (size_t)kWalkMaxNodes * 2;
+  b += 128;                                    // unoriented-cycle list: count + kWalkMaxUnoriented ids
+  return b;
+}
+
+// The cycle a vertex lies on (leftmost vertex, i.e. orbit label with bit 0 cleared) and whether that
+// cycle owns an oriented grey edge: walk to the next start of a walk and read its converged word,
+// or get round an orbit that has none.
+__device__ inline unsigned walk_cycle_of(const uint16_t *H, const uint32_t *NW, const uint16_t *MAP,
+                                         unsigned v, unsigned mask, int shift, unsigned &oriented) {
+  unsigned x = v, mn = v, orr = 0;
+  for (;;) {
+    if ((x & mask) == 0u) {
+      const unsigned id = MAP[x >> shift];
+      if (id != 0xFFFFu) {
+        const uint32_t w = NW[id];
+        oriented = ((orr & 1u) | ((w >> 1) & 1u));
+        return (w >> 17) & ~1u;
+      }
+    }
+    const unsigned nx = H[x + 1] & 0x7FFFu;
+    orr |= x ^ nx;
+    x = nx;
+    if (x == v) { oriented = orr & 1u; return mn & ~1u; }
+    mn = min(mn, x);
+  }
+}
+
+// Ends of gamma's gene g in pi (vertices): tail[a-1] = where gene +a begins.  Positions past the
+// last gene hold the sentinel gene n+1, whose tail entry is the frame vertex 2n+1 (its "left end").
+__device__ inline void walk_ends(const uint16_t *tail, int g, unsigned &L, unsigned &R) {
+  const unsigned v = tail[(g > 0 ? g : -g) - 1];
+  const unsigned h = ((v - 1u) ^ 1u) + 1u;
+  L = (g > 0) ? v : h;
+  R = (g > 0) ? h : v;
+}
+
+// Genes t0 .. t0+7 of a row (n+1 past the end): two 16-byte loads when the row allows it.
+__device__ inline void walk_load8(const int32_t *gamma, int t0, int n, bool vec, int (&G)[8]) {
+#ifndef GRSR_EMU
+  if (vec && t0 + 8 <= n) {
+    const int4 a = __ldg((const int4 *)(gamma + t0)), b = __ldg((const int4 *)(gamma + t0 + 4));
+    G[0] = a.x; G[1] = a.y; G[2] = a.z; G[3] = a.w; G[4] = b.x; G[5] = b.y; G[6] = b.z; G[7] = b.w;
+    return;
+  }
+#else
+  (void)vec;
+#endif
+#pragma unroll
+  for (int k = 0; k < 8; k++) G[k] = (t0 + k < n) ? gamma[t0 + k] : n + 1;
+}
+
+// Pointer jumping over the first 32 * NJ walk words (ids >= W are words that point at themselves),
+// then the roots: a walk whose own segment holds the minimum of its orbit.  Counts the cycles (roots
+// with an even label) and lists the unoriented ones in UL.
+template <int NJ>
+__device__ inline void walk_jump(uint32_t *NW, uint32_t *UL, int W, int lane, unsigned &ncyc, unsigned &nun) {
+  uint32_t Rg[NJ], seg[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int id = lane + 32 * j;
+    if (id < W) Rg[j] = NW[id];
+    else { Rg[j] = GRSR_W_MAKE(0x7FFFu, id, GRSR_W_ADJ); NW[id] = Rg[j]; }
+    seg[j] = Rg[j] >> 17;
+  }
+  __syncwarp();
+  const int rounds = ceil_log2(W);
+  const char *Nb = (const char *)NW;
+  for (int r = 0; r < rounds; r++) {
+    uint32_t chg = 0, U[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) U[j] = *(const uint32_t *)(Nb + (Rg[j] & 0x1FFFCu));
+    GRSR_EMU_READ_BEFORE_WRITE_WARP();
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const uint32_t w = Rg[j], wu = U[j];
+      const uint32_t nw = (min(w, wu) & 0xFFFE0000u) | (wu & 0x1FFFFu) | (w & GRSR_W_ORBIT);
+      chg |= (nw ^ w);
+      Rg[j] = nw;
+      NW[lane + 32 * j] = nw;
+    }
+    __syncwarp();
+    if (!__any_sync(kFull, (chg & 0xFFFE0002u) != 0u)) break;
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const uint32_t w = Rg[j];
+    const unsigned label = w >> 17;
+    if (!(w & GRSR_W_ADJ) && seg[j] == label && !(label & 1u)) {   // root of the orbit of a cycle's leftmost vertex
+      ncyc++;
+      if (!(w & GRSR_W_ORBIT)) {
+        nun++;
+        const unsigned k = atomicAdd(&UL[0], 1u);
+        if (k < (unsigned)kWalkMaxUnoriented) UL[1 + k] = label;
+      }
+    }
+  }
+}
+
+// One warp, one pair at a time.  Warp w of the launch owns the contiguous pairs
+// [w * chunk, (w+1) * chunk); tail[] stays staged while consecutive pairs share their pi row.
+// stride 1: out[p] = d; stride 5: {d,b,c,h,f}.  Deferred pairs: defer_list[atomicAdd(defer_count)] = p.
+__global__ void __launch_bounds__(256)
+dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                 const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
+                 int stride, int shift, int32_t *defer_list, unsigned *defer_count) {
+  GRSR_DYN_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int S = 2 * n + 2;
+  const int hwords = walk_hwords(n);
+  unsigned char *base = smem_raw + (size_t)wid * walk_warp_bytes(n);
+  uint16_t *tail = (uint16_t *)base;                 base += walk_tail_bytes(n);
+  uint32_t *Hw = (uint32_t *)base;                   base += (size_t)hwords * 4;
+  uint32_t *NW = (uint32_t *)base;                   base += (size_t)kWalkMaxWalks * 4;
+  uint16_t *MAP = (uint16_t *)base;                  base += (size_t)kWalkMaxNodes * 2;
+  uint32_t *UL = (uint32_t *)base;                   // [0] count, [1..] leftmost vertices
+  uint16_t *H = (uint16_t *)Hw;
+  const unsigned mask = (1u << shift) - 1u;
+  const int K = (S + (int)mask) >> shift;            // nodes 0 .. K-1 <-> vertices i << shift
+  const bool vec = ((n & 3) == 0) && ((((size_t)genomes) & 15) == 0);
+
+  // pads of H (never rewritten): entry 0, entry S+1 and the words up to the 4-word multiple;
+  // the sentinel gene's tail entry
+  for (int w = (n + 1) + lane; w < hwords; w += 32) Hw[w] = 0x80008000u;
+  if (lane == 0) { H[0] = (uint16_t)kVis; tail[n] = (uint16_t)(S - 1); }
+  __syncwarp();
+
+  const long long nwarps = (long long)gridDim.x * wpb;
+  const long long chunk = (npairs + nwarps - 1) / nwarps;
+  const long long p0 = ((long long)blockIdx.x * wpb + wid) * chunk;
+  const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
+  int staged = -1;
+
+  for (long long p = p0; p < p1; p++) {
+    const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
+    if (pj != staged) {
+      const int32_t *sp = sinv + (long long)pj * n;
+      for (int i = lane; i < n; i += 32) {
+        const int s = sp[i];
+        tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
+      }
+      staged = pj;
+    }
+    if (lane == 0) UL[0] = 0;
+    {
+      uint32_t *M32 = (uint32_t *)MAP;                  // no walk starts anywhere yet
+      for (int j = lane; j < (K + 1) / 2; j += 32) M32[j] = 0xFFFFFFFFu;
+    }
+    __syncwarp();
+
+    // ---- phase A: lane owns genes cb + 8*lane .. +7 of gamma; L/R = left/right end in pi ----------
+    const int32_t *gamma = genomes + (long long)gi * n;
+    unsigned nadj = 0;
+    {
+      int G[8], Gn[8];
+      walk_load8(gamma, 8 * lane, n, vec, G);
+      unsigned carry = 0;                               // right end of the gene before this chunk (vertex 0 first)
+      for (int cb = 0; cb < n; cb += 256) {
+        const int tb = cb + 8 * lane;
+        walk_load8(gamma, tb + 256, n, vec, Gn);
+        unsigned L[8], R[8], Lx, Rx;
+#pragma unroll
+        for (int k = 0; k < 8; k++) walk_ends(tail, G[k], L[k], R[k]);
+        walk_ends(tail, Gn[0], Lx, Rx);
+        (void)Rx;
+        unsigned pr = __shfl_up_sync(kFull, R[7], 1);
+        if (lane == 0) pr = carry;
+        const unsigned nl0 = __shfl_sync(kFull, Lx, 0);
+        unsigned nl = __shfl_down_sync(kFull, L[0], 1);
+        if (lane == 31) nl = nl0;
+        carry = __shfl_sync(kFull, R[7], 31);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const unsigned Lt = L[k], Rt = R[k];
+          const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
+          const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
+          const bool real = (tb + k < n);
+          const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
+          nadj += (adjL && real) ? 1u : 0u;
+          const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
+          const bool fwd = (Lt & 1u) != 0u;                             // L_t = 2p+1: its entry is the low half
+          const unsigned word = fwd ? (ea | (eb << 16)) : (eb | (ea << 16));
+          if (real) Hw[(Lt + Rt + 1u) >> 2] = word;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) G[k] = Gn[k];
+      }
+      if (lane == 0) {                                  // the two frame vertices and grey edge n
+        unsigned L0, R0, Ll, Rl;
+        walk_ends(tail, gamma[0], L0, R0);
+        walk_ends(tail, gamma[n - 1], Ll, Rl);
+        H[1] = (uint16_t)((L0 ^ 1u) | ((L0 == 1u) ? kVis : 0u));         // tau(0) = L_0 ^ 1
+        const bool adjn = ((Rl ^ 1u) == (unsigned)S - 1u);
+        H[S] = (uint16_t)((Rl ^ 1u) | (adjn ? kVis : 0u));              // tau(2n+1) = R_{n-1} ^ 1
+        nadj += adjn ? 1u : 0u;
+      }
+    }
+    __syncwarp();
+
+    // ---- walks -------------------------------------------------------------------------------------
+    // A lane without a walk points at the pad entry H[0] (x = nx = -1): a step from there, like a
+    // step of a walk that has ended, changes nothing, so the steps need no "am I walking" test.
+    int W = 0;                                          // walks started so far (warp-uniform)
+    {
+      int ci = lane - 32, myid = -1;
+      bool done = false, ended = true;
+      unsigned x = 0xFFFFFFFFu, nx = 0xFFFFFFFFu, mn = 0, orr = 0, e = kVis;
+      for (;;) {
+        // start section: close the walk that has ended, claim the next free node of my list
+        if (ended && myid >= 0) {
+          NW[myid] = GRSR_W_MAKE(mn, MAP[nx >> shift], (orr & 1u) ? GRSR_W_ORBIT : 0u);
+          myid = -1;
+          x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
+        }
+        const bool want = ended && !done;
+        if (want) {
+          for (;;) {
+            ci += 32;
+            if (ci >= K) { done = true; break; }
+            e = H[((unsigned)ci << shift) + 1];
+            if (!(e & kVis)) break;
+          }
+        }
+        const bool got = want && !done;
+        const unsigned m = __ballot_sync(kFull, got);
+        if (got) {
+          myid = W + __popc(m & lt_mask);
+          if (myid < kWalkMaxWalks) {
+            x = (unsigned)ci << shift;
+            H[x + 1] = (uint16_t)(e | kVis);
+            MAP[ci] = (uint16_t)myid;
+            nx = e; mn = x; orr = 0; ended = false;
+          } else {                                      // walk table full: the leftover pass or tier 2 decides
+            myid = -1; done = true;
+          }
+        }
+        W += __popc(m);
+        __syncwarp();
+        if (!__any_sync(kFull, !ended)) break;
+        for (;;) {
+#pragma unroll
+          for (int s = 0; s < kWalkGroup; s++) {
+            const unsigned u = nx;
+            orr |= x ^ u;
+            e = H[u + 1];
+            if (!(e & kVis)) { H[u + 1] = (uint16_t)(e | kVis); mn = min(mn, u); x = u; nx = e; }
+          }
+          ended = (e & kVis) != 0u;
+          const unsigned walking = __ballot_sync(kFull, !ended);
+          const unsigned idle = __ballot_sync(kFull, ended && !done);
+          if (walking == 0u || __popc(idle) >= kWalkIdle) break;
+        }
+        __syncwarp();                                   // no lane scans for a free node while others still claim
+      }
+      W = min(W, kWalkMaxWalks);
+    }
+    __syncwarp();
+
+    // ---- jumping over the walk words -----------------------------------------------------------------
+    unsigned ncyc = 0, nun = 0;
+    if (W <= 128) walk_jump<4>(NW, UL, W, lane, ncyc, nun);
+    else walk_jump<8>(NW, UL, W, lane, ncyc, nun);
+
+    // ---- orbits without a node: the unmarked vertices ------------------------------------------------
+    int defer = 0;
+    {
+      int budget = kWalkLeftoverBudget;
+      const uint4 *H4 = (const uint4 *)Hw;
+      for (int q = lane; q < (hwords >> 2); q += 32) {
+        const uint4 x = H4[q];
+        if (((x.x & x.y & x.z & x.w) & 0x80008000u) == 0x80008000u) continue;
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+          if (ent & kVis) continue;
+          const unsigned u0 = (unsigned)(8 * q + k) - 1u;          // vertex of entry 8q+k
+          unsigned x1 = ent, orr = u0 ^ ent;
+          bool root = true;
+          while (x1 != u0) {
+            if (x1 < u0) { root = false; break; }                  // a smaller vertex owns this orbit
+            if (--budget < 0) { root = false; defer = 1; break; }
+            const unsigned nx = H[x1 + 1] & 0x7FFFu;
+            orr |= x1 ^ nx;
+            x1 = nx;
+          }
+          if (root && !(u0 & 1u)) {
+            ncyc++;
+            if (!(orr & 1u)) {
+              nun++;
+              const unsigned kk = atomicAdd(&UL[0], 1u);
+              if (kk < (unsigned)kWalkMaxUnoriented) UL[1 + kk] = u0;
+            }
+          }
+        }
+      }
+    }
+    nadj = __reduce_add_sync(kFull, nadj);
+    ncyc = __reduce_add_sync(kFull, ncyc);
+    nun = __reduce_add_sync(kFull, nun);
+    defer = __any_sync(kFull, defer);
+    __syncwarp();
+    const int b = (n + 1) - (int)nadj, c = (int)ncyc;
+
+    // ---- unoriented cycles: the "covered by an oriented cycle" test of dist_core -------------------
+    if (!defer && nun != 0u) {
+      if (nun > (unsigned)kWalkMaxUnoriented) defer = 1;
+      for (unsigned k = 0; k < nun && !defer; k++) {
+        const unsigned qq = UL[1 + k];
+        bool hit = false;
+        for (int it = 0; it < 8; it++) {
+          const unsigned v = qq + 2u + 32u * it + lane;
+          int st = 2;                                   // past the last vertex: stop
+          if (v < (unsigned)S) {
+            st = 0;
+            const unsigned ent = H[v + 1];
+            if ((ent & 0x7FFFu) != v) {                 // not an adjacency end
+              unsigned ori;
+              const unsigned cy = walk_cycle_of(H, NW, MAP, v, mask, shift, ori);
+              if (cy == qq) st = 2;                     // Q's own next vertex: the probe ends here
+              else if (cy < qq && ori) st = 1;          // an oriented cycle that starts left of Q
+            }
+          }
+          const unsigned mh = __ballot_sync(kFull, st == 1), ms = __ballot_sync(kFull, st == 2);
+          if (mh | ms) { hit = mh && (!ms || __ffs((int)mh) < __ffs((int)ms)); break; }
+        }
+        if (!hit) defer = 1;
+      }
+    }
+
+    if (lane == 0) {
+      if (defer) {
+        defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
+      } else if (stride == 1) {
+        out[p] = b - c;
+      } else {
+        int32_t *o = out + 5 * p; o[0] = b - c; o[1] = b; o[2] = c; o[3] = 0; o[4] = 0;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Second tier: the pairs the walk kernel deferred, through dist_core (block per pair).
+template <int NT, int EPT>
+__global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
+dist_deferred_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                     const int32_t *__restrict__ pairs, const int32_t *__restrict__ defer_list,
+                     const unsigned *__restrict__ defer_count, int32_t *__restrict__ out, int stride) {
+  GRSR_DYN_SMEM(smem_raw);
+  Work wk;
+  work_carve(wk, smem_raw, n, NT * EPT, false);
+  uint16_t *stage = (uint16_t *)(smem_raw + work_bytes(n, NT * EPT, false));
+  const long long total = (long long)*defer_count;
+  int staged = -1;
+  for (long long q = blockIdx.x; q < total; q += gridDim.x) {
+    const long long p = defer_list[q];
+    const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
+    if (pj != staged) {
+      __syncthreads();
+      const int32_t *sp = sinv + (long long)pj * n;
+      for (int i = threadIdx.x; i < n; i += NT) {
+        const int s = sp[i];
+        stage[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);
+      }
+      staged = pj;
+      __syncthreads();
+    }
+    EndsFromRows ends; ends.gamma = genomes + (long long)gi * n; ends.tail = stage;
+    Stats st = dist_core<NT, EPT, false>(wk, n, ends);
+    if (threadIdx.x == 0) {
+      if (stride == 1) out[p] = st.d;
+      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
+    }
+  }
+}
+
+} // namespace grsr

@@ -6,6 +6,7 @@
 #include "../../grsr_b200/csrc/grsr_core.cuh"
 #include "../../grsr_b200/csrc/grsr_scenario.cuh"
 #include "../../grsr_b200/csrc/grsr_stepwise.cuh"
+#include "../../grsr_b200/csrc/grsr_walk.cuh"
 #include <vector>
 
 extern "C" int emu_dist_pairs(const int32_t *genomes, int G, int n, const int32_t *pairs,
@@ -151,5 +152,33 @@ extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int
                                      (unsigned long long *)nullptr, &ticket, 1);
   }));
   for (int p = 0; p < npairs; p++) if (status[p] == 0) status[p] = st2[p];
+  return 0;
+}
+
+// two-tier distance path: warp-per-pair walk kernel, then the block-per-pair kernel on the pairs it
+// deferred (same sequence as grsr_dist_pairs_dev); *deferred = how many pairs took the second tier
+extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const int32_t *pairs,
+                                   long long npairs, int32_t *out, int stride, int wpb, int grid,
+                                   int *deferred) {
+  std::vector<int32_t> sinv((size_t)G * n);
+  long long total = (long long)G * n;
+  int32_t *sp = sinv.data();
+  emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
+  int shift = grsr::walk_shift(n);
+  std::vector<int32_t> dl((size_t)npairs + 1, -1);
+  unsigned dc = 0;
+  int32_t *dlp = dl.data();
+  unsigned *dcp = &dc;
+  size_t smem = grsr::walk_warp_bytes(n) * (size_t)wpb;
+  emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
+    grsr::dist_walk_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp);
+  });
+  *deferred = (int)dc;
+  int t, e;
+  grsr::pick_shape(n, 0, &t, &e);
+  size_t smem2 = grsr::work_bytes(n, t * e, false) + grsr::stage_bytes(n);
+  GRSR_DISPATCH_SHAPE(t, e, emu::launch(3, (unsigned)t, smem2, [&] {
+    grsr::dist_deferred_kernel<kNt, kEpt>(genomes, sp, n, pairs, dlp, dcp, out, stride);
+  }));
   return 0;
 }

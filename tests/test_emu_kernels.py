@@ -131,3 +131,45 @@ def test_emulated_stepwise_scenarios():
                 want, _ = U.orc_scenario(srcs[q], dsts[q])
                 assert status[q] == 0 and np.array_equal(steps[q], want)
             assert n < 5 or stepwise_steps > 0
+
+
+# ---- the two-tier distance path: warp-per-pair walk kernel + deferred pairs -------------------------
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_emulated_walk_exhaustive(n):
+    perms = U.all_signed_perms(n)
+    g = np.vstack([np.arange(1, n + 1, dtype=np.int32)[None, :], perms])
+    k = len(g)
+    pairs = np.array([[0, i] for i in range(1, k)] + [[i, 0] for i in range(1, k)], dtype=np.int32)
+    got, _ = U.emu_stats_walk(g, pairs, 2, 2)
+    assert np.array_equal(got, U.orc_stats(g, pairs))
+
+
+@pytest.mark.parametrize("n,wpb", [(5, 1), (7, 2), (15, 1), (16, 4), (33, 2), (63, 1), (64, 2), (127, 3),
+                                    (255, 1), (256, 2), (300, 2), (600, 1), (1100, 2), (2100, 1)])
+def test_emulated_walk_structured(n, wpb):
+    """every node-stride / words-per-lane shape; hurdle-rich rows are deferred to the second tier,
+    random ones are settled by the walk kernel"""
+    g = U.mixed_genomes(n, 12 if n < 200 else (6 if n < 2000 else 4), seed=n)
+    pairs = _ordered(len(g))
+    got, deferred = U.emu_stats_walk(g, pairs, wpb, 2)
+    want = U.orc_stats(g, pairs)
+    assert np.array_equal(got, want)
+    easy = int(np.sum((want[:, 3] == 0)))
+    assert deferred <= len(pairs) - easy // 2      # the first tier settles most hurdle-free pairs
+
+
+def test_emulated_walk_random_pairs_not_deferred():
+    rng = random.Random(11)
+    g = np.asarray([gen.random_signed_perm(400, rng) for _ in range(12)], dtype=np.int32)
+    pairs = _ordered(len(g))
+    got, deferred = U.emu_stats_walk(g, pairs, 2, 3)
+    assert np.array_equal(got, U.orc_stats(g, pairs))
+    assert deferred <= len(pairs) // 20
+
+
+def test_emulated_walk_fortress_fixture():
+    z = np.load(U.GOLDEN + "/stats_mixed.npz")
+    g = z["gfort"]
+    got, _ = U.emu_stats_walk(g, _ordered(len(g)), 2, 2)
+    assert np.array_equal(got, z["sfort"])

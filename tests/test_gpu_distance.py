@@ -109,3 +109,33 @@ def test_rejects_bad_input():
     with pytest.raises(capi.GrsrError) as e:
         capi.dist_matrix(np.array([[1, 2, 3]], dtype=np.int32), first_device=0, ngpus=99)
     assert e.value.code == capi.ERR_NODEVICE
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [29, 200, 500, 2000, 4500])
+def test_two_tier_path_equals_block_per_pair_path(n, monkeypatch):
+    """The warp-per-pair walk kernel + deferred second tier (GRSR_WALK=1) and the block-per-pair kernel
+    alone (GRSR_WALK=0) must give identical {d,b,c,h,f}; the oracle checks a sample."""
+    from grsr_b200 import capi
+    g = U.mixed_genomes(n, 24 if n <= 2000 else 12, seed=1000 + n)
+    pairs = np.array([[i, j] for i in range(len(g)) for j in range(len(g))], dtype=np.int32)
+    monkeypatch.setenv("GRSR_WALK", "1")
+    two = capi.dist_pairs(g, pairs, stats=True)
+    monkeypatch.setenv("GRSR_WALK", "0")
+    one = capi.dist_pairs(g, pairs, stats=True)
+    assert np.array_equal(two, one)
+    sample = pairs[:: max(1, len(pairs) // 60)]
+    monkeypatch.setenv("GRSR_WALK", "1")
+    assert np.array_equal(capi.dist_pairs(g, sample, stats=True), U.orc_stats(g, sample))
+
+
+@pytest.mark.gpu
+def test_two_tier_path_exhaustive_n6(monkeypatch):
+    from grsr_b200 import capi
+    monkeypatch.setenv("GRSR_WALK", "1")
+    n = 6
+    perms = U.all_signed_perms(n)
+    g = np.vstack([np.arange(1, n + 1, dtype=np.int32)[None, :], perms])
+    k = len(g)
+    pairs = np.array([[0, i] for i in range(1, k)] + [[i, 0] for i in range(1, k)], dtype=np.int32)
+    assert np.array_equal(capi.dist_pairs(g, pairs, stats=True), U.orc_stats(g, pairs))
