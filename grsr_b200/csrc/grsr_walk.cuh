@@ -333,21 +333,44 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
     if (W <= 128) walk_jump<4>(NW, UL, W, lane, ncyc, nun);
     else walk_jump<8>(NW, UL, W, lane, ncyc, nun);
 
-    // ---- orbits without a node: the unmarked vertices ------------------------------------------------
+    // ---- orbits without a node: list the unclaimed vertices, then one lane per vertex ---------------
+    // The list lives in the upper half of the walk words (free when at most 128 walks were started).
     int defer = 0;
     {
-      int budget = kWalkLeftoverBudget;
+      uint16_t *LL = (uint16_t *)(NW + 128);
+      const unsigned llcap = (W <= 128) ? 256u : 0u;
+      if (lane == 0) UL[31] = 0;
+      __syncwarp();
       const uint4 *H4 = (const uint4 *)Hw;
-      for (int q = lane; q < (hwords >> 2); q += 32) {
-        const uint4 x = H4[q];
-        if (((x.x & x.y & x.z & x.w) & 0x80008000u) == 0x80008000u) continue;
-        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+      const int hq = hwords >> 2;
+      for (int q0 = 0; q0 < hq; q0 += 32) {
+        const int q = q0 + lane;
+        uint4 x;
+        x.x = x.y = x.z = x.w = 0x80008000u;
+        if (q < hq) x = H4[q];
+        const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
+        if (__any_sync(kFull, some)) {
+          if (some) {
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-          if (ent & kVis) continue;
-          const unsigned u0 = (unsigned)(8 * q + k) - 1u;          // vertex of entry 8q+k
-          unsigned x1 = ent, orr = u0 ^ ent;
+            for (int k = 0; k < 8; k++) {
+              const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+              if (!(ent & kVis)) {
+                const unsigned pos = atomicAdd(&UL[31], 1u);
+                if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);   // vertex of entry 8q+k
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      const unsigned cnt = UL[31];
+      if (cnt > llcap) defer = 1;
+      else {
+        int budget = kWalkLeftoverBudget;
+        for (unsigned i = lane; i < cnt; i += 32) {
+          const unsigned u0 = LL[i];
+          unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
           bool root = true;
           while (x1 != u0) {
             if (x1 < u0) { root = false; break; }                  // a smaller vertex owns this orbit
