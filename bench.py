@@ -323,7 +323,9 @@ def run_gpu_arm(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": "grsr::dist_pairs_kernel", "kernel_ms": kernel_ms,
+                    "traffic": traffic,
+                    "kernel": "grsr::dist_walk_shared_kernel (+ walk_order_kernel, dist_deferred_kernel on the deferred pairs)",
+                    "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "pairs_per_launch": cnt, "peak_source": peak_src}
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -343,7 +345,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(genomes.nbytes) * world,
                     "d2h_bytes_per_step": int(P * 4), "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "grsr_dist_matrix_shard (host buffers, pinned)"},
-            "gpu_launches": args.steps * world, "clocks": clocks, "scenario": scen,
+            "gpu_launches": 4 * args.steps * world, "clocks": clocks, "scenario": scen,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

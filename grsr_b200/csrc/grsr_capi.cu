@@ -132,24 +132,28 @@ int finish_plan(K kernel, long long units, Launch &L) {
 }
 
 // Plan of the warp-per-pair first tier (grsr_walk.cuh): warps per block chosen so that the most
-// warps stay resident per SM; grid = whole resident waves.
+// warps stay resident per SM; grid = whole resident waves.  shared = the kernel whose warps share one
+// staged pi row per block (pair lists sorted by pi row).
 struct WalkPlan { int shift; int wpb; int grid; size_t smem; int warps_per_sm; };
 
-int plan_walk(int n, long long npairs, WalkPlan &P) {
+template <class K>
+int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   int dev;
   CK(cudaGetDevice(&dev));
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  auto kernel = grsr::dist_walk_kernel;
-  const size_t wb = grsr::walk_warp_bytes(n);
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                           (int)cudaSharedmemCarveoutMaxShared));
   int best_wpb = 0, best_occ = 0;
-  const int forced = env_int("GRSR_WALK_WPB", 0);
-  for (int wpb = 8; wpb >= 1; wpb >>= 1) {
+  const int forced = env_int(shared ? "GRSR_WALK_SHARED_WPB" : "GRSR_WALK_WPB", 0);
+  // equal warps per SM: the private-row kernel prefers few large blocks (less reserved shared
+  // memory), the shared-row kernel many small ones (a block waits for its slowest warp at every run)
+  for (int k = 0; k < (shared ? 32 : 8); k++) {
+    const int wpb = shared ? k + 1 : 8 - k;
     if (forced && wpb != forced) continue;
-    const size_t smem = wb * wpb;
+    const size_t smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * wpb
+                               : grsr::walk_warp_bytes(n) * wpb;
     if (smem > (size_t)di.smem_optin) continue;
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
@@ -162,7 +166,10 @@ int plan_walk(int n, long long npairs, WalkPlan &P) {
   P.shift = grsr::walk_shift(n);
   int fs = env_int("GRSR_WALK_SHIFT", 0);
   if (fs >= P.shift && fs <= 10) P.shift = fs;
-  P.wpb = best_wpb; P.smem = wb * best_wpb; P.warps_per_sm = best_wpb * best_occ;
+  P.wpb = best_wpb;
+  P.smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * best_wpb
+                  : grsr::walk_warp_bytes(n) * best_wpb;
+  P.warps_per_sm = best_wpb * best_occ;
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   long long g = (long long)di.sms * best_occ, need = (npairs + best_wpb - 1) / best_wpb;
   if (g > need) g = need;
@@ -659,8 +666,11 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
   const int walk_mode = env_int("GRSR_WALK", -1);
   if (small_fits(num_genes, false) && walk_mode != 0 && (walk_mode == 1 || npairs >= di0.sms) &&
       dev0 < kMaxDevices && npairs < (1ll << 31)) {
-    WalkPlan WP;
-    if ((rc = plan_walk(num_genes, npairs, WP))) return rc;
+    // order_mode: -1 = decide on the device (walk_order_kernel), 0 = private rows, 1 = shared rows
+    const int order_mode = env_int("GRSR_WALK_SHARED", -1);
+    WalkPlan WP, WS;
+    if (order_mode != 1 && (rc = plan_walk(grsr::dist_walk_kernel, false, num_genes, npairs, WP))) return rc;
+    if (order_mode != 0 && (rc = plan_walk(grsr::dist_walk_shared_kernel, true, num_genes, npairs, WS))) return rc;
     Launch L;
     grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
     L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
@@ -673,10 +683,17 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
       if ((rc = cache_reserve(c, 7, 256 + (size_t)npairs * sizeof(int32_t), &dq))) return rc;
     }
     unsigned *dcount = (unsigned *)dq;
+    unsigned *dflag = (order_mode < 0) ? (unsigned *)((char *)dq + 64) : nullptr;
     int32_t *dlist = (int32_t *)((char *)dq + 256);
-    CK(cudaMemsetAsync(dcount, 0, sizeof(unsigned), (cudaStream_t)stream));
-    grsr::dist_walk_kernel<<<WP.grid, WP.wpb * 32, WP.smem, (cudaStream_t)stream>>>(
-        d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WP.shift, dlist, dcount);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(dcount, 0, sizeof(unsigned), st));
+    if (dflag) grsr::walk_order_kernel<<<1, 1024, 0, st>>>(d_pairs, (long long)npairs, dflag);
+    if (order_mode != 0)
+      grsr::dist_walk_shared_kernel<<<WS.grid, WS.wpb * 32, WS.smem, st>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WS.shift, dlist, dcount, dflag);
+    if (order_mode != 1)
+      grsr::dist_walk_kernel<<<WP.grid, WP.wpb * 32, WP.smem, st>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WP.shift, dlist, dcount, dflag);
     CK(cudaGetLastError());
     GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_deferred_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
         d_genomes, d_sinv, num_genes, d_pairs, dlist, dcount, d_out, stride)));

@@ -168,33 +168,290 @@ __device__ inline void walk_jump(uint32_t *NW, uint32_t *UL, int W, int lane, un
   }
 }
 
-// One warp, one pair at a time.  Warp w of the launch owns the contiguous pairs
-// [w * chunk, (w+1) * chunk); tail[] stays staged while consecutive pairs share their pi row.
-// stride 1: out[p] = d; stride 5: {d,b,c,h,f}.  Deferred pairs: defer_list[atomicAdd(defer_count)] = p.
-__global__ void __launch_bounds__(256)
-dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
-                 const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
-                 int stride, int shift, int32_t *defer_list, unsigned *defer_count) {
-  GRSR_DYN_SMEM(smem_raw);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+// Per-warp working set in shared memory.
+struct WalkMem {
+  const uint16_t *tail;     // [n+1] staged pi row (vertex where gene +a begins) + the sentinel entry
+  uint32_t *Hw;             // successor table, 32-bit view ([walk_hwords])
+  uint32_t *NW;             // [kWalkMaxWalks] walk words
+  uint16_t *MAP;            // [kWalkMaxNodes] node -> walk id
+  uint32_t *UL;             // [32] unoriented-cycle list and counters
+};
+
+__host__ __device__ inline size_t walk_private_bytes(int n) {
+  return (size_t)walk_hwords(n) * 4 + (size_t)kWalkMaxWalks * 4 + (size_t)kWalkMaxNodes * 2 + 128;
+}
+
+__device__ inline void walk_carve_private(WalkMem &wm, unsigned char *base, int n) {
+  wm.Hw = (uint32_t *)base;   base += (size_t)walk_hwords(n) * 4;
+  wm.NW = (uint32_t *)base;   base += (size_t)kWalkMaxWalks * 4;
+  wm.MAP = (uint16_t *)base;  base += (size_t)kWalkMaxNodes * 2;
+  wm.UL = (uint32_t *)base;
+}
+
+// pads of H (never rewritten): entry 0, entry S+1 and the words up to the 4-word multiple
+__device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
+  const int hwords = walk_hwords(n);
+  for (int w = (n + 1) + lane; w < hwords; w += 32) wm.Hw[w] = 0x80008000u;
+  if (lane == 0) ((uint16_t *)wm.Hw)[0] = (uint16_t)kVis;
+}
+
+// One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
+// in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
+__device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
+                                 long long p, int32_t *__restrict__ out, int stride, int shift,
+                                 int32_t *defer_list, unsigned *defer_count) {
+  const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int S = 2 * n + 2;
   const int hwords = walk_hwords(n);
-  unsigned char *base = smem_raw + (size_t)wid * walk_warp_bytes(n);
-  uint16_t *tail = (uint16_t *)base;                 base += walk_tail_bytes(n);
-  uint32_t *Hw = (uint32_t *)base;                   base += (size_t)hwords * 4;
-  uint32_t *NW = (uint32_t *)base;                   base += (size_t)kWalkMaxWalks * 4;
-  uint16_t *MAP = (uint16_t *)base;                  base += (size_t)kWalkMaxNodes * 2;
-  uint32_t *UL = (uint32_t *)base;                   // [0] count, [1..] leftmost vertices
+  const uint16_t *tail = wm.tail;
+  uint32_t *Hw = wm.Hw, *NW = wm.NW, *UL = wm.UL;
+  uint16_t *MAP = wm.MAP;
   uint16_t *H = (uint16_t *)Hw;
   const unsigned mask = (1u << shift) - 1u;
   const int K = (S + (int)mask) >> shift;            // nodes 0 .. K-1 <-> vertices i << shift
   const bool vec = ((n & 3) == 0) && ((((size_t)genomes) & 15) == 0);
 
-  // pads of H (never rewritten): entry 0, entry S+1 and the words up to the 4-word multiple;
-  // the sentinel gene's tail entry
-  for (int w = (n + 1) + lane; w < hwords; w += 32) Hw[w] = 0x80008000u;
-  if (lane == 0) { H[0] = (uint16_t)kVis; tail[n] = (uint16_t)(S - 1); }
+  if (lane == 0) UL[0] = 0;
+  {
+    uint32_t *M32 = (uint32_t *)MAP;                  // no walk starts anywhere yet
+    for (int j = lane; j < (K + 1) / 2; j += 32) M32[j] = 0xFFFFFFFFu;
+  }
+  __syncwarp();
+
+  // ---- phase A: lane owns genes cb + 8*lane .. +7 of gamma; L/R = left/right end in pi ----------
+  const int32_t *gamma = genomes + (long long)gi * n;
+  unsigned nadj = 0;
+  {
+    int G[8], Gn[8];
+    walk_load8(gamma, 8 * lane, n, vec, G);
+    unsigned carry = 0;                               // right end of the gene before this chunk (vertex 0 first)
+    for (int cb = 0; cb < n; cb += 256) {
+      const int tb = cb + 8 * lane;
+      walk_load8(gamma, tb + 256, n, vec, Gn);
+      unsigned L[8], R[8], Lx, Rx;
+#pragma unroll
+      for (int k = 0; k < 8; k++) walk_ends(tail, G[k], L[k], R[k]);
+      walk_ends(tail, Gn[0], Lx, Rx);
+      (void)Rx;
+      unsigned pr = __shfl_up_sync(kFull, R[7], 1);
+      if (lane == 0) pr = carry;
+      const unsigned nl0 = __shfl_sync(kFull, Lx, 0);
+      unsigned nl = __shfl_down_sync(kFull, L[0], 1);
+      if (lane == 31) nl = nl0;
+      carry = __shfl_sync(kFull, R[7], 31);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const unsigned Lt = L[k], Rt = R[k];
+        const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
+        const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
+        const bool real = (tb + k < n);
+        const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
+        nadj += (adjL && real) ? 1u : 0u;
+        const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
+        const bool fwd = (Lt & 1u) != 0u;                             // L_t = 2p+1: its entry is the low half
+        const unsigned word = fwd ? (ea | (eb << 16)) : (eb | (ea << 16));
+        if (real) Hw[(Lt + Rt + 1u) >> 2] = word;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) G[k] = Gn[k];
+    }
+    if (lane == 0) {                                  // the two frame vertices and grey edge n
+      unsigned L0, R0, Ll, Rl;
+      walk_ends(tail, gamma[0], L0, R0);
+      walk_ends(tail, gamma[n - 1], Ll, Rl);
+      H[1] = (uint16_t)((L0 ^ 1u) | ((L0 == 1u) ? kVis : 0u));         // tau(0) = L_0 ^ 1
+      const bool adjn = ((Rl ^ 1u) == (unsigned)S - 1u);
+      H[S] = (uint16_t)((Rl ^ 1u) | (adjn ? kVis : 0u));              // tau(2n+1) = R_{n-1} ^ 1
+      nadj += adjn ? 1u : 0u;
+    }
+  }
+  __syncwarp();
+
+  // ---- walks -------------------------------------------------------------------------------------
+  // A lane without a walk points at the pad entry H[0] (x = nx = -1): a step from there, like a
+  // step of a walk that has ended, changes nothing, so the steps need no "am I walking" test.
+  int W = 0;                                          // walks started so far (warp-uniform)
+  {
+    int ci = lane - 32, myid = -1;
+    bool done = false, ended = true;
+    unsigned x = 0xFFFFFFFFu, nx = 0xFFFFFFFFu, mn = 0, orr = 0, e = kVis;
+    for (;;) {
+      // start section: close the walk that has ended, claim the next free node of my list
+      if (ended && myid >= 0) {
+        NW[myid] = GRSR_W_MAKE(mn, MAP[nx >> shift], (orr & 1u) ? GRSR_W_ORBIT : 0u);
+        myid = -1;
+        x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
+      }
+      const bool want = ended && !done;
+      if (want) {
+        for (;;) {
+          ci += 32;
+          if (ci >= K) { done = true; break; }
+          e = H[((unsigned)ci << shift) + 1];
+          if (!(e & kVis)) break;
+        }
+      }
+      const bool got = want && !done;
+      const unsigned m = __ballot_sync(kFull, got);
+      if (got) {
+        myid = W + __popc(m & lt_mask);
+        if (myid < kWalkMaxWalks) {
+          x = (unsigned)ci << shift;
+          H[x + 1] = (uint16_t)(e | kVis);
+          MAP[ci] = (uint16_t)myid;
+          nx = e; mn = x; orr = 0; ended = false;
+        } else {                                      // walk table full: the leftover pass or tier 2 decides
+          myid = -1; done = true;
+        }
+      }
+      W += __popc(m);
+      __syncwarp();
+      if (!__any_sync(kFull, !ended)) break;
+      for (;;) {
+#pragma unroll
+        for (int s = 0; s < kWalkGroup; s++) {
+          const unsigned u = nx;
+          orr |= x ^ u;
+          e = H[u + 1];
+          if (!(e & kVis)) { H[u + 1] = (uint16_t)(e | kVis); mn = min(mn, u); x = u; nx = e; }
+        }
+        ended = (e & kVis) != 0u;
+        const unsigned walking = __ballot_sync(kFull, !ended);
+        const unsigned idle = __ballot_sync(kFull, ended && !done);
+        if (walking == 0u || __popc(idle) >= kWalkIdle) break;
+      }
+      __syncwarp();                                   // no lane scans for a free node while others still claim
+    }
+    W = min(W, kWalkMaxWalks);
+  }
+  __syncwarp();
+
+  // ---- jumping over the walk words -----------------------------------------------------------------
+  unsigned ncyc = 0, nun = 0;
+  if (W <= 128) walk_jump<4>(NW, UL, W, lane, ncyc, nun);
+  else walk_jump<8>(NW, UL, W, lane, ncyc, nun);
+
+  // ---- orbits without a node: list the unclaimed vertices, then one lane per vertex ---------------
+  // The list lives in the upper half of the walk words (free when at most 128 walks were started).
+  int defer = 0;
+  {
+    uint16_t *LL = (uint16_t *)(NW + 128);
+    const unsigned llcap = (W <= 128) ? 256u : 0u;
+    if (lane == 0) UL[31] = 0;
+    __syncwarp();
+    const uint4 *H4 = (const uint4 *)Hw;
+    const int hq = hwords >> 2;
+    for (int q0 = 0; q0 < hq; q0 += 32) {
+      const int q = q0 + lane;
+      uint4 x;
+      x.x = x.y = x.z = x.w = 0x80008000u;
+      if (q < hq) x = H4[q];
+      const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
+      if (__any_sync(kFull, some)) {
+        if (some) {
+          const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if (!(ent & kVis)) {
+              const unsigned pos = atomicAdd(&UL[31], 1u);
+              if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);   // vertex of entry 8q+k
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const unsigned cnt = UL[31];
+    if (cnt > llcap) defer = 1;
+    else {
+      int budget = kWalkLeftoverBudget;
+      for (unsigned i = lane; i < cnt; i += 32) {
+        const unsigned u0 = LL[i];
+        unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
+        bool root = true;
+        while (x1 != u0) {
+          if (x1 < u0) { root = false; break; }                  // a smaller vertex owns this orbit
+          if (--budget < 0) { root = false; defer = 1; break; }
+          const unsigned nx = H[x1 + 1] & 0x7FFFu;
+          orr |= x1 ^ nx;
+          x1 = nx;
+        }
+        if (root && !(u0 & 1u)) {
+          ncyc++;
+          if (!(orr & 1u)) {
+            nun++;
+            const unsigned kk = atomicAdd(&UL[0], 1u);
+            if (kk < (unsigned)kWalkMaxUnoriented) UL[1 + kk] = u0;
+          }
+        }
+      }
+    }
+  }
+  nadj = __reduce_add_sync(kFull, nadj);
+  ncyc = __reduce_add_sync(kFull, ncyc);
+  nun = __reduce_add_sync(kFull, nun);
+  defer = __any_sync(kFull, defer);
+  __syncwarp();
+  const int b = (n + 1) - (int)nadj, c = (int)ncyc;
+
+  // ---- unoriented cycles: the "covered by an oriented cycle" test of dist_core -------------------
+  if (!defer && nun != 0u) {
+    if (nun > (unsigned)kWalkMaxUnoriented) defer = 1;
+    for (unsigned k = 0; k < nun && !defer; k++) {
+      const unsigned qq = UL[1 + k];
+      bool hit = false;
+      for (int it = 0; it < 8; it++) {
+        const unsigned v = qq + 2u + 32u * it + lane;
+        int st = 2;                                   // past the last vertex: stop
+        if (v < (unsigned)S) {
+          st = 0;
+          const unsigned ent = H[v + 1];
+          if ((ent & 0x7FFFu) != v) {                 // not an adjacency end
+            unsigned ori;
+            const unsigned cy = walk_cycle_of(H, NW, MAP, v, mask, shift, ori);
+            if (cy == qq) st = 2;                     // Q's own next vertex: the probe ends here
+            else if (cy < qq && ori) st = 1;          // an oriented cycle that starts left of Q
+          }
+        }
+        const unsigned mh = __ballot_sync(kFull, st == 1), ms = __ballot_sync(kFull, st == 2);
+        if (mh | ms) { hit = mh && (!ms || __ffs((int)mh) < __ffs((int)ms)); break; }
+      }
+      if (!hit) defer = 1;
+    }
+  }
+
+  if (lane == 0) {
+    if (defer) {
+      defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
+    } else if (stride == 1) {
+      out[p] = b - c;
+    } else {
+      int32_t *o = out + 5 * p; o[0] = b - c; o[1] = b; o[2] = c; o[3] = 0; o[4] = 0;
+    }
+  }
+  __syncwarp();
+}
+
+// One warp, one pair at a time, every warp with its own staged pi row: warp w of the launch owns the
+// contiguous pairs [w * chunk, (w+1) * chunk); tail[] stays staged while consecutive pairs share
+// their pi row.  Serves pair lists in any order.
+__global__ void __launch_bounds__(256)
+dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                 const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
+                 int stride, int shift, int32_t *defer_list, unsigned *defer_count,
+                 const unsigned *__restrict__ order_flag) {
+  if (order_flag && *order_flag != 0u) return;        // the list is pi-sorted: the shared-row kernel runs
+  GRSR_DYN_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  unsigned char *base = smem_raw + (size_t)wid * walk_warp_bytes(n);
+  uint16_t *tail = (uint16_t *)base;
+  WalkMem wm;
+  wm.tail = tail;
+  walk_carve_private(wm, base + walk_tail_bytes(n), n);
+  walk_init_private(wm, n, lane);
+  if (lane == 0) tail[n] = (uint16_t)(2 * n + 1);     // the sentinel gene's entry
   __syncwarp();
 
   const long long nwarps = (long long)gridDim.x * wpb;
@@ -202,7 +459,6 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   const long long p0 = ((long long)blockIdx.x * wpb + wid) * chunk;
   const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
   int staged = -1;
-
   for (long long p = p0; p < p1; p++) {
     const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
     if (pj != staged) {
@@ -212,228 +468,71 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
         tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
       }
       staged = pj;
-    }
-    if (lane == 0) UL[0] = 0;
-    {
-      uint32_t *M32 = (uint32_t *)MAP;                  // no walk starts anywhere yet
-      for (int j = lane; j < (K + 1) / 2; j += 32) M32[j] = 0xFFFFFFFFu;
-    }
-    __syncwarp();
-
-    // ---- phase A: lane owns genes cb + 8*lane .. +7 of gamma; L/R = left/right end in pi ----------
-    const int32_t *gamma = genomes + (long long)gi * n;
-    unsigned nadj = 0;
-    {
-      int G[8], Gn[8];
-      walk_load8(gamma, 8 * lane, n, vec, G);
-      unsigned carry = 0;                               // right end of the gene before this chunk (vertex 0 first)
-      for (int cb = 0; cb < n; cb += 256) {
-        const int tb = cb + 8 * lane;
-        walk_load8(gamma, tb + 256, n, vec, Gn);
-        unsigned L[8], R[8], Lx, Rx;
-#pragma unroll
-        for (int k = 0; k < 8; k++) walk_ends(tail, G[k], L[k], R[k]);
-        walk_ends(tail, Gn[0], Lx, Rx);
-        (void)Rx;
-        unsigned pr = __shfl_up_sync(kFull, R[7], 1);
-        if (lane == 0) pr = carry;
-        const unsigned nl0 = __shfl_sync(kFull, Lx, 0);
-        unsigned nl = __shfl_down_sync(kFull, L[0], 1);
-        if (lane == 31) nl = nl0;
-        carry = __shfl_sync(kFull, R[7], 31);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const unsigned Lt = L[k], Rt = R[k];
-          const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
-          const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
-          const bool real = (tb + k < n);
-          const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
-          nadj += (adjL && real) ? 1u : 0u;
-          const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
-          const bool fwd = (Lt & 1u) != 0u;                             // L_t = 2p+1: its entry is the low half
-          const unsigned word = fwd ? (ea | (eb << 16)) : (eb | (ea << 16));
-          if (real) Hw[(Lt + Rt + 1u) >> 2] = word;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) G[k] = Gn[k];
-      }
-      if (lane == 0) {                                  // the two frame vertices and grey edge n
-        unsigned L0, R0, Ll, Rl;
-        walk_ends(tail, gamma[0], L0, R0);
-        walk_ends(tail, gamma[n - 1], Ll, Rl);
-        H[1] = (uint16_t)((L0 ^ 1u) | ((L0 == 1u) ? kVis : 0u));         // tau(0) = L_0 ^ 1
-        const bool adjn = ((Rl ^ 1u) == (unsigned)S - 1u);
-        H[S] = (uint16_t)((Rl ^ 1u) | (adjn ? kVis : 0u));              // tau(2n+1) = R_{n-1} ^ 1
-        nadj += adjn ? 1u : 0u;
-      }
-    }
-    __syncwarp();
-
-    // ---- walks -------------------------------------------------------------------------------------
-    // A lane without a walk points at the pad entry H[0] (x = nx = -1): a step from there, like a
-    // step of a walk that has ended, changes nothing, so the steps need no "am I walking" test.
-    int W = 0;                                          // walks started so far (warp-uniform)
-    {
-      int ci = lane - 32, myid = -1;
-      bool done = false, ended = true;
-      unsigned x = 0xFFFFFFFFu, nx = 0xFFFFFFFFu, mn = 0, orr = 0, e = kVis;
-      for (;;) {
-        // start section: close the walk that has ended, claim the next free node of my list
-        if (ended && myid >= 0) {
-          NW[myid] = GRSR_W_MAKE(mn, MAP[nx >> shift], (orr & 1u) ? GRSR_W_ORBIT : 0u);
-          myid = -1;
-          x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
-        }
-        const bool want = ended && !done;
-        if (want) {
-          for (;;) {
-            ci += 32;
-            if (ci >= K) { done = true; break; }
-            e = H[((unsigned)ci << shift) + 1];
-            if (!(e & kVis)) break;
-          }
-        }
-        const bool got = want && !done;
-        const unsigned m = __ballot_sync(kFull, got);
-        if (got) {
-          myid = W + __popc(m & lt_mask);
-          if (myid < kWalkMaxWalks) {
-            x = (unsigned)ci << shift;
-            H[x + 1] = (uint16_t)(e | kVis);
-            MAP[ci] = (uint16_t)myid;
-            nx = e; mn = x; orr = 0; ended = false;
-          } else {                                      // walk table full: the leftover pass or tier 2 decides
-            myid = -1; done = true;
-          }
-        }
-        W += __popc(m);
-        __syncwarp();
-        if (!__any_sync(kFull, !ended)) break;
-        for (;;) {
-#pragma unroll
-          for (int s = 0; s < kWalkGroup; s++) {
-            const unsigned u = nx;
-            orr |= x ^ u;
-            e = H[u + 1];
-            if (!(e & kVis)) { H[u + 1] = (uint16_t)(e | kVis); mn = min(mn, u); x = u; nx = e; }
-          }
-          ended = (e & kVis) != 0u;
-          const unsigned walking = __ballot_sync(kFull, !ended);
-          const unsigned idle = __ballot_sync(kFull, ended && !done);
-          if (walking == 0u || __popc(idle) >= kWalkIdle) break;
-        }
-        __syncwarp();                                   // no lane scans for a free node while others still claim
-      }
-      W = min(W, kWalkMaxWalks);
-    }
-    __syncwarp();
-
-    // ---- jumping over the walk words -----------------------------------------------------------------
-    unsigned ncyc = 0, nun = 0;
-    if (W <= 128) walk_jump<4>(NW, UL, W, lane, ncyc, nun);
-    else walk_jump<8>(NW, UL, W, lane, ncyc, nun);
-
-    // ---- orbits without a node: list the unclaimed vertices, then one lane per vertex ---------------
-    // The list lives in the upper half of the walk words (free when at most 128 walks were started).
-    int defer = 0;
-    {
-      uint16_t *LL = (uint16_t *)(NW + 128);
-      const unsigned llcap = (W <= 128) ? 256u : 0u;
-      if (lane == 0) UL[31] = 0;
       __syncwarp();
-      const uint4 *H4 = (const uint4 *)Hw;
-      const int hq = hwords >> 2;
-      for (int q0 = 0; q0 < hq; q0 += 32) {
-        const int q = q0 + lane;
-        uint4 x;
-        x.x = x.y = x.z = x.w = 0x80008000u;
-        if (q < hq) x = H4[q];
-        const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
-        if (__any_sync(kFull, some)) {
-          if (some) {
-            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-              const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-              if (!(ent & kVis)) {
-                const unsigned pos = atomicAdd(&UL[31], 1u);
-                if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);   // vertex of entry 8q+k
-              }
-            }
-          }
-        }
-      }
-      __syncwarp();
-      const unsigned cnt = UL[31];
-      if (cnt > llcap) defer = 1;
-      else {
-        int budget = kWalkLeftoverBudget;
-        for (unsigned i = lane; i < cnt; i += 32) {
-          const unsigned u0 = LL[i];
-          unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
-          bool root = true;
-          while (x1 != u0) {
-            if (x1 < u0) { root = false; break; }                  // a smaller vertex owns this orbit
-            if (--budget < 0) { root = false; defer = 1; break; }
-            const unsigned nx = H[x1 + 1] & 0x7FFFu;
-            orr |= x1 ^ nx;
-            x1 = nx;
-          }
-          if (root && !(u0 & 1u)) {
-            ncyc++;
-            if (!(orr & 1u)) {
-              nun++;
-              const unsigned kk = atomicAdd(&UL[0], 1u);
-              if (kk < (unsigned)kWalkMaxUnoriented) UL[1 + kk] = u0;
-            }
-          }
-        }
-      }
     }
-    nadj = __reduce_add_sync(kFull, nadj);
-    ncyc = __reduce_add_sync(kFull, ncyc);
-    nun = __reduce_add_sync(kFull, nun);
-    defer = __any_sync(kFull, defer);
-    __syncwarp();
-    const int b = (n + 1) - (int)nadj, c = (int)ncyc;
-
-    // ---- unoriented cycles: the "covered by an oriented cycle" test of dist_core -------------------
-    if (!defer && nun != 0u) {
-      if (nun > (unsigned)kWalkMaxUnoriented) defer = 1;
-      for (unsigned k = 0; k < nun && !defer; k++) {
-        const unsigned qq = UL[1 + k];
-        bool hit = false;
-        for (int it = 0; it < 8; it++) {
-          const unsigned v = qq + 2u + 32u * it + lane;
-          int st = 2;                                   // past the last vertex: stop
-          if (v < (unsigned)S) {
-            st = 0;
-            const unsigned ent = H[v + 1];
-            if ((ent & 0x7FFFu) != v) {                 // not an adjacency end
-              unsigned ori;
-              const unsigned cy = walk_cycle_of(H, NW, MAP, v, mask, shift, ori);
-              if (cy == qq) st = 2;                     // Q's own next vertex: the probe ends here
-              else if (cy < qq && ori) st = 1;          // an oriented cycle that starts left of Q
-            }
-          }
-          const unsigned mh = __ballot_sync(kFull, st == 1), ms = __ballot_sync(kFull, st == 2);
-          if (mh | ms) { hit = mh && (!ms || __ffs((int)mh) < __ffs((int)ms)); break; }
-        }
-        if (!hit) defer = 1;
-      }
-    }
-
-    if (lane == 0) {
-      if (defer) {
-        defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
-      } else if (stride == 1) {
-        out[p] = b - c;
-      } else {
-        int32_t *o = out + 5 * p; o[0] = b - c; o[1] = b; o[2] = c; o[3] = 0; o[4] = 0;
-      }
-    }
-    __syncwarp();
+    walk_pair(wm, genomes, n, gi, p, out, stride, shift, defer_list, defer_count);
   }
+}
+
+// The same for pair lists sorted by pi row (the column-by-column triangle of a distance matrix): the
+// warps of a block share ONE staged pi row, which leaves room for more resident warps per SM.  A block
+// owns a contiguous chunk of the list and goes through it one run of equal pi rows at a time.
+__global__ void __launch_bounds__(1024)
+dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
+                        const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
+                        int stride, int shift, int32_t *defer_list, unsigned *defer_count,
+                        const unsigned *__restrict__ order_flag) {
+  if (order_flag && *order_flag == 0u) return;        // not sorted: the private-row kernel runs
+  GRSR_DYN_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  unsigned *s_end = (unsigned *)smem_raw;             // first 16 bytes: run length found by the block
+  uint16_t *tail = (uint16_t *)(smem_raw + 16);
+  WalkMem wm;
+  wm.tail = tail;
+  walk_carve_private(wm, smem_raw + 16 + walk_tail_bytes(n) + (size_t)wid * walk_private_bytes(n), n);
+  walk_init_private(wm, n, lane);
+  if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n + 1);
+
+  const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
+  const long long b0 = (long long)blockIdx.x * chunk;
+  const long long b1 = (b0 + chunk < npairs) ? b0 + chunk : npairs;
+  for (long long p = b0; p < b1;) {
+    const int pj = pairs[2 * p + 1];
+    const unsigned left = (unsigned)(b1 - p);
+    __syncthreads();                                   // everybody is done with the previous run
+    if (threadIdx.x == 0) *s_end = left;
+    __syncthreads();
+    for (unsigned qb = 0; qb < left; qb += blockDim.x) {
+      const unsigned q = qb + threadIdx.x;
+      const bool diff = q < left && pairs[2 * (p + q) + 1] != pj;
+      if (diff) atomicMin(s_end, q);
+      if (__syncthreads_or(diff)) break;
+    }
+    const int32_t *sp = sinv + (long long)pj * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int s = sp[i];
+      tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);
+    }
+    __syncthreads();
+    const unsigned run = *s_end;
+    for (unsigned q = wid; q < run; q += wpb)
+      walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shift, defer_list, defer_count);
+    p += run;
+  }
+}
+
+// Decides which of the two kernels serves a list: *order_flag = 1 when runs of equal pi rows are
+// long (at most one change per 64 pairs on average), else 0.  One block.
+__global__ void walk_order_kernel(const int32_t *__restrict__ pairs, long long npairs, unsigned *order_flag) {
+  __shared__ unsigned changes;
+  if (threadIdx.x == 0) changes = 0;
+  __syncthreads();
+  unsigned c = 0;
+  for (long long q = threadIdx.x; q + 1 < npairs; q += blockDim.x)
+    c += (pairs[2 * q + 1] != pairs[2 * q + 3]) ? 1u : 0u;
+  atomicAdd(&changes, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *order_flag = ((unsigned long long)changes * 64ull <= (unsigned long long)npairs) ? 1u : 0u;
 }
 
 // Second tier: the pairs the walk kernel deferred, through dist_core (block per pair).

@@ -165,14 +165,16 @@ def emu_stats(genomes, pairs, threads: int = 64, grid: int = 2, large: bool = Fa
     return out
 
 
-def emu_stats_walk(genomes, pairs, wpb: int = 2, grid: int = 2):
-    """Two-tier distance path (walk kernel + deferred pairs) in the emulator: (stats, #deferred)."""
+def emu_stats_walk(genomes, pairs, wpb: int = 2, grid: int = 2, shared: int = 0):
+    """Two-tier distance path (walk kernel + deferred pairs) in the emulator: (stats, #deferred).
+    shared: 0 = every warp stages its own pi row, 1 = the warps of a block share one, -1 = decided
+    by walk_order_kernel as in the library."""
     g = _i32(genomes)
     pr = _i32(pairs).reshape(-1, 2)
     out = np.full((len(pr), 5), -7, dtype=np.int32)
     deferred = ctypes.c_int(0)
     emulator().emu_dist_pairs_walk(_p(g), g.shape[0], g.shape[1], _p(pr), ctypes.c_longlong(len(pr)),
-                                   _p(out), 5, wpb, grid, ctypes.byref(deferred))
+                                   _p(out), 5, wpb, grid, ctypes.byref(deferred), shared)
     return out, deferred.value
 
 

@@ -155,24 +155,34 @@ extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int
   return 0;
 }
 
-// two-tier distance path: warp-per-pair walk kernel, then the block-per-pair kernel on the pairs it
-// deferred (same sequence as grsr_dist_pairs_dev); *deferred = how many pairs took the second tier
+// two-tier distance path: warp-per-pair walk kernels (shared = -1: walk_order_kernel decides between
+// the private-row and the shared-row kernel, as grsr_dist_pairs_dev does; 0 / 1 force one), then the
+// block-per-pair kernel on the pairs they deferred; *deferred = how many pairs took the second tier
 extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const int32_t *pairs,
                                    long long npairs, int32_t *out, int stride, int wpb, int grid,
-                                   int *deferred) {
+                                   int *deferred, int shared) {
   std::vector<int32_t> sinv((size_t)G * n);
   long long total = (long long)G * n;
   int32_t *sp = sinv.data();
   emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
   int shift = grsr::walk_shift(n);
   std::vector<int32_t> dl((size_t)npairs + 1, -1);
-  unsigned dc = 0;
+  unsigned dc = 0, flag = 0;
   int32_t *dlp = dl.data();
-  unsigned *dcp = &dc;
-  size_t smem = grsr::walk_warp_bytes(n) * (size_t)wpb;
-  emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
-    grsr::dist_walk_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp);
-  });
+  unsigned *dcp = &dc, *fp = (shared < 0) ? &flag : nullptr;
+  if (fp) emu::launch(1, 64, 0, [&] { grsr::walk_order_kernel(pairs, npairs, fp); });
+  if (shared != 0) {
+    size_t smem = 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * (size_t)wpb;
+    emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
+      grsr::dist_walk_shared_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp);
+    });
+  }
+  if (shared != 1) {
+    size_t smem = grsr::walk_warp_bytes(n) * (size_t)wpb;
+    emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
+      grsr::dist_walk_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp);
+    });
+  }
   *deferred = (int)dc;
   int t, e;
   grsr::pick_shape(n, 0, &t, &e);
@@ -180,5 +190,5 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   GRSR_DISPATCH_SHAPE(t, e, emu::launch(3, (unsigned)t, smem2, [&] {
     grsr::dist_deferred_kernel<kNt, kEpt>(genomes, sp, n, pairs, dlp, dcp, out, stride);
   }));
-  return 0;
+  return shared < 0 ? (int)flag : 0;
 }

@@ -173,3 +173,19 @@ def test_emulated_walk_fortress_fixture():
     g = z["gfort"]
     got, _ = U.emu_stats_walk(g, _ordered(len(g)), 2, 2)
     assert np.array_equal(got, z["sfort"])
+
+
+@pytest.mark.parametrize("n,wpb", [(3, 2), (9, 3), (40, 2), (129, 3), (300, 2)])
+def test_emulated_walk_shared_rows(n, wpb):
+    """the kernel whose warps share one staged pi row per block, on a pi-sorted list (column-by-column
+    triangle, runs of every length) and -- forced -- on an unsorted one; automatic choice by
+    walk_order_kernel gives the same numbers"""
+    g = U.mixed_genomes(n, 14, seed=50 + n)
+    tri = np.array([[i, j] for j in range(len(g)) for i in range(j)], dtype=np.int32)
+    want = U.orc_stats(g, tri)
+    for shared in (1, -1, 0):
+        got, _ = U.emu_stats_walk(g, tri, wpb, 3, shared=shared)
+        assert np.array_equal(got, want), shared
+    sq = _ordered(len(g))
+    got, _ = U.emu_stats_walk(g, sq, wpb, 2, shared=1)
+    assert np.array_equal(got, U.orc_stats(g, sq))
