@@ -145,10 +145,12 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   if (rc) return rc;
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                           (int)cudaSharedmemCarveoutMaxShared));
+  // The private-row kernel takes the shape with the most resident warps (few large blocks first: less
+  // reserved shared memory).  In the shared-row kernel a block waits for its slowest warp at every run
+  // of equal pi rows, so it takes the SMALLEST block that reaches 90 % of the best warp count.
   int best_wpb = 0, best_occ = 0;
   const int forced = env_int(shared ? "GRSR_WALK_SHARED_WPB" : "GRSR_WALK_WPB", 0);
-  // equal warps per SM: the private-row kernel prefers few large blocks (less reserved shared
-  // memory), the shared-row kernel many small ones (a block waits for its slowest warp at every run)
+  int occ_of[33] = {0};
   for (int k = 0; k < (shared ? 32 : 8); k++) {
     const int wpb = shared ? k + 1 : 8 - k;
     if (forced && wpb != forced) continue;
@@ -158,8 +160,12 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, wpb * 32, smem));
+    occ_of[wpb] = occ;
     if (occ * wpb > best_occ * best_wpb) { best_wpb = wpb; best_occ = occ; }
   }
+  if (shared && best_wpb)
+    for (int wpb = 1; wpb < best_wpb; wpb++)
+      if (occ_of[wpb] * wpb * 10 >= best_occ * best_wpb * 9) { best_wpb = wpb; best_occ = occ_of[wpb]; break; }
   if (!best_wpb) return fail(GRSR_ERR_TOOLARGE, "walk kernel does not fit on an SM (n=%d)", n);
   int cap = env_int("GRSR_WALK_OCC", best_occ);
   if (cap >= 1 && cap < best_occ) best_occ = cap;

@@ -106,6 +106,13 @@ __device__ inline void walk_ends(const uint16_t *tail, int g, unsigned &L, unsig
   R = (g > 0) ? h : v;
 }
 
+// (hi16 << 16) | lo16 of two 16-bit values
+#ifdef GRSR_EMU
+__device__ inline unsigned walk_pack(unsigned lo16, unsigned hi16) { return (lo16 & 0xFFFFu) | (hi16 << 16); }
+#else
+__device__ inline unsigned walk_pack(unsigned lo16, unsigned hi16) { return __byte_perm(lo16, hi16, 0x5410); }
+#endif
+
 // Genes t0 .. t0+7 of a row (n+1 past the end): two 16-byte loads when the row allows it.
 __device__ inline void walk_load8(const int32_t *gamma, int t0, int n, bool vec, int (&G)[8]) {
 #ifndef GRSR_EMU
@@ -249,9 +256,9 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
         const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
         nadj += (adjL && real) ? 1u : 0u;
         const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
-        const bool fwd = (Lt & 1u) != 0u;                             // L_t = 2p+1: its entry is the low half
-        const unsigned word = fwd ? (ea | (eb << 16)) : (eb | (ea << 16));
-        if (real) Hw[(Lt + Rt + 1u) >> 2] = word;
+        const bool fwd = Lt < Rt;                                     // L_t = 2p+1: its entry is the low half
+        const unsigned word = walk_pack(fwd ? ea : eb, fwd ? eb : ea);
+        if (real) *(uint32_t *)((char *)Hw + Lt + Rt + 1u) = word;    // L_t + R_t + 1 = 4(p+1): word p+1
       }
 #pragma unroll
       for (int k = 0; k < 8; k++) G[k] = Gn[k];
@@ -284,12 +291,19 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
         x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
       }
       const bool want = ended && !done;
-      if (want) {
+      if (want) {                                       // four list entries per round trip to shared memory
         for (;;) {
-          ci += 32;
-          if (ci >= K) { done = true; break; }
-          e = H[((unsigned)ci << shift) + 1];
-          if (!(e & kVis)) break;
+          const int c0 = ci + 32, c1 = ci + 64, c2 = ci + 96, c3 = ci + 128;
+          if (c0 >= K) { done = true; break; }
+          const unsigned e0 = H[((unsigned)c0 << shift) + 1];
+          const unsigned e1 = (c1 < K) ? H[((unsigned)c1 << shift) + 1] : kVis;
+          const unsigned e2 = (c2 < K) ? H[((unsigned)c2 << shift) + 1] : kVis;
+          const unsigned e3 = (c3 < K) ? H[((unsigned)c3 << shift) + 1] : kVis;
+          if (!(e0 & kVis)) { ci = c0; e = e0; break; }
+          if (!(e1 & kVis)) { ci = c1; e = e1; break; }
+          if (!(e2 & kVis)) { ci = c2; e = e2; break; }
+          if (!(e3 & kVis)) { ci = c3; e = e3; break; }
+          ci = c3;
         }
       }
       const bool got = want && !done;
@@ -350,14 +364,16 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
       if (__any_sync(kFull, some)) {
         if (some) {
-          const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            const unsigned ent = (xs[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if (!(ent & kVis)) {
-              const unsigned pos = atomicAdd(&UL[31], 1u);
-              if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);   // vertex of entry 8q+k
-            }
+          // bit k of um <-> entry 8q+k unclaimed
+          const unsigned y0 = ~x.x & 0x80008000u, y1 = ~x.y & 0x80008000u;
+          const unsigned y2 = ~x.z & 0x80008000u, y3 = ~x.w & 0x80008000u;
+          unsigned um = ((y0 >> 15) & 1u) | ((y0 >> 30) & 2u) | ((y1 >> 13) & 4u) | ((y1 >> 28) & 8u) |
+                        ((y2 >> 11) & 16u) | ((y2 >> 26) & 32u) | ((y3 >> 9) & 64u) | ((y3 >> 24) & 128u);
+          while (um) {
+            const int k = __ffs((int)um) - 1;
+            um &= um - 1u;
+            const unsigned pos = atomicAdd(&UL[31], 1u);
+            if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);     // vertex of entry 8q+k
           }
         }
       }
