@@ -172,6 +172,9 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   P.shift = grsr::walk_shift(n);
   int fs = env_int("GRSR_WALK_SHIFT", 0);
   if (fs >= P.shift && fs <= 10) P.shift = fs;
+  int idle = env_int("GRSR_WALK_IDLE", grsr::kWalkIdle);
+  if (idle < 1 || idle > 32) idle = grsr::kWalkIdle;
+  P.shift = grsr::walk_shape_arg(P.shift, idle);
   P.wpb = best_wpb;
   P.smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * best_wpb
                   : grsr::walk_warp_bytes(n) * best_wpb;

@@ -49,7 +49,7 @@ static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a wal
 static const int kWalkMaxNodes = 512;        // nodes (possible walk starts) per pair
 static const int kWalkMaxWalks = 256;        // walks per pair (8 words per lane in the jumping phase)
 static const int kWalkGroup = 4;             // tau steps between two votes
-static const int kWalkIdle = 8;              // lanes that must be out of work before new walks start
+static const int kWalkIdle = 12;             // default: lanes that must be out of work before new walks start
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
 static const int kWalkLeftoverBudget = 1536; // steps a lane may spend on orbits without a node
 
@@ -60,6 +60,9 @@ __host__ __device__ inline int walk_shift(int n) {
   while (((S + (1 << sh) - 1) >> sh) > kWalkMaxNodes) sh++;
   return sh;
 }
+
+// kernel argument: node stride and start threshold in one int
+__host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return shift | (idle_min << 8); }
 
 __host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 3) & ~3; }   // 32-bit words of H
 
@@ -205,8 +208,9 @@ __device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
 // One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
 // in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
 __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
-                                 long long p, int32_t *__restrict__ out, int stride, int shift,
+                                 long long p, int32_t *__restrict__ out, int stride, int shape,
                                  int32_t *defer_list, unsigned *defer_count) {
+  const int shift = shape & 0xFF, idle_min = shape >> 8;   // node stride 2^shift; lanes out of work before new walks start
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int S = 2 * n + 2;
@@ -333,7 +337,7 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
         ended = (e & kVis) != 0u;
         const unsigned walking = __ballot_sync(kFull, !ended);
         const unsigned idle = __ballot_sync(kFull, ended && !done);
-        if (walking == 0u || __popc(idle) >= kWalkIdle) break;
+        if (walking == 0u || __popc(idle) >= idle_min) break;
       }
       __syncwarp();                                   // no lane scans for a free node while others still claim
     }
@@ -456,7 +460,7 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
 __global__ void __launch_bounds__(256)
 dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                  const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
-                 int stride, int shift, int32_t *defer_list, unsigned *defer_count,
+                 int stride, int shape, int32_t *defer_list, unsigned *defer_count,
                  const unsigned *__restrict__ order_flag) {
   if (order_flag && *order_flag != 0u) return;        // the list is pi-sorted: the shared-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
@@ -486,7 +490,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
       staged = pj;
       __syncwarp();
     }
-    walk_pair(wm, genomes, n, gi, p, out, stride, shift, defer_list, defer_count);
+    walk_pair(wm, genomes, n, gi, p, out, stride, shape, defer_list, defer_count);
   }
 }
 
@@ -496,7 +500,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
 __global__ void __launch_bounds__(1024)
 dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                         const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
-                        int stride, int shift, int32_t *defer_list, unsigned *defer_count,
+                        int stride, int shape, int32_t *defer_list, unsigned *defer_count,
                         const unsigned *__restrict__ order_flag) {
   if (order_flag && *order_flag == 0u) return;        // not sorted: the private-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
@@ -532,7 +536,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
     __syncthreads();
     const unsigned run = *s_end;
     for (unsigned q = wid; q < run; q += wpb)
-      walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shift, defer_list, defer_count);
+      walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shape, defer_list, defer_count);
     p += run;
   }
 }

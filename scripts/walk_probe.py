@@ -22,7 +22,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def run(env, reps=5):
-    for k in ("GRSR_WALK", "GRSR_WALK_WPB", "GRSR_WALK_OCC", "GRSR_WALK_SHIFT", "GRSR_WALK_SHARED", "GRSR_WALK_SHARED_WPB"):
+    for k in ("GRSR_WALK", "GRSR_WALK_WPB", "GRSR_WALK_OCC", "GRSR_WALK_SHIFT", "GRSR_WALK_SHARED", "GRSR_WALK_SHARED_WPB", "GRSR_WALK_IDLE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     out = torch.full((P,), -1, dtype=torch.int32, device=dev)
@@ -43,9 +43,10 @@ def run(env, reps=5):
 
 base_ms, base = run({"GRSR_WALK": "0"})
 print("block-per-pair      %.3f ms  %.3e pairs/s" % (base_ms, P / base_ms * 1e3), flush=True)
-envs = [{"GRSR_WALK": "1"}, {"GRSR_WALK": "1", "GRSR_WALK_SHARED": "0"}]
-for w in (4, 5, 7, 10, 11, 16, 22):
-    envs.append({"GRSR_WALK": "1", "GRSR_WALK_SHARED": "1", "GRSR_WALK_SHARED_WPB": str(w)})
+envs = [{"GRSR_WALK": "1"}]
+for sh in (3, 4):
+    for idle in (4, 6, 8, 12, 16):
+        envs.append({"GRSR_WALK": "1", "GRSR_WALK_SHIFT": str(sh), "GRSR_WALK_IDLE": str(idle)})
 for env in envs:
     try:
         ms, out = run(env)

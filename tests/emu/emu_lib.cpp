@@ -165,7 +165,7 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   long long total = (long long)G * n;
   int32_t *sp = sinv.data();
   emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
-  int shift = grsr::walk_shift(n);
+  int shift = grsr::walk_shape_arg(grsr::walk_shift(n), grsr::kWalkIdle);
   std::vector<int32_t> dl((size_t)npairs + 1, -1);
   unsigned dc = 0, flag = 0;
   int32_t *dlp = dl.data();
