@@ -695,8 +695,11 @@ int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num
     unsigned *dflag = (order_mode < 0) ? (unsigned *)((char *)dq + 64) : nullptr;
     int32_t *dlist = (int32_t *)((char *)dq + 256);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(dcount, 0, sizeof(unsigned), st));
-    if (dflag) grsr::walk_order_kernel<<<1, 1024, 0, st>>>(d_pairs, (long long)npairs, dflag);
+    CK(cudaMemsetAsync(dq, 0, 128, st));               // deferred count and pi-row change count
+    if (dflag) {
+      long long ob = (npairs + 255) / 256;
+      grsr::walk_order_kernel<<<(int)(ob < 592 ? ob : 592), 256, 0, st>>>(d_pairs, (long long)npairs, dflag);
+    }
     if (order_mode != 0)
       grsr::dist_walk_shared_kernel<<<WS.grid, WS.wpb * 32, WS.smem, st>>>(
           d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WS.shift, dlist, dcount, dflag);

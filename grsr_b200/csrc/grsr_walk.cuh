@@ -454,6 +454,11 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   __syncwarp();
 }
 
+// Verdict of walk_order_kernel: runs of equal pi rows are long (at most one change per 64 pairs).
+__device__ inline bool walk_list_sorted(const unsigned *changes, long long npairs) {
+  return (unsigned long long)*changes * 64ull <= (unsigned long long)npairs;
+}
+
 // One warp, one pair at a time, every warp with its own staged pi row: warp w of the launch owns the
 // contiguous pairs [w * chunk, (w+1) * chunk); tail[] stays staged while consecutive pairs share
 // their pi row.  Serves pair lists in any order.
@@ -462,7 +467,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
                  const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                  int stride, int shape, int32_t *defer_list, unsigned *defer_count,
                  const unsigned *__restrict__ order_flag) {
-  if (order_flag && *order_flag != 0u) return;        // the list is pi-sorted: the shared-row kernel runs
+  if (order_flag && walk_list_sorted(order_flag, npairs)) return;   // pi-sorted list: the shared-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   unsigned char *base = smem_raw + (size_t)wid * walk_warp_bytes(n);
@@ -502,7 +507,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
                         const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                         int stride, int shape, int32_t *defer_list, unsigned *defer_count,
                         const unsigned *__restrict__ order_flag) {
-  if (order_flag && *order_flag == 0u) return;        // not sorted: the private-row kernel runs
+  if (order_flag && !walk_list_sorted(order_flag, npairs)) return;  // not sorted: the private-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   unsigned *s_end = (unsigned *)smem_raw;             // first 16 bytes: run length found by the block
@@ -541,18 +546,16 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   }
 }
 
-// Decides which of the two kernels serves a list: *order_flag = 1 when runs of equal pi rows are
-// long (at most one change per 64 pairs on average), else 0.  One block.
-__global__ void walk_order_kernel(const int32_t *__restrict__ pairs, long long npairs, unsigned *order_flag) {
-  __shared__ unsigned changes;
-  if (threadIdx.x == 0) changes = 0;
-  __syncthreads();
+// Decides which of the two kernels serves a list: counts the positions where the pi row changes
+// (*changes must be zero at launch).  Runs of equal pi rows are "long" when there is at most one
+// change per 64 pairs on average (walk_list_sorted).
+__global__ void walk_order_kernel(const int32_t *__restrict__ pairs, long long npairs, unsigned *changes) {
   unsigned c = 0;
-  for (long long q = threadIdx.x; q + 1 < npairs; q += blockDim.x)
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q + 1 < npairs; q += stride)
     c += (pairs[2 * q + 1] != pairs[2 * q + 3]) ? 1u : 0u;
-  atomicAdd(&changes, c);
-  __syncthreads();
-  if (threadIdx.x == 0) *order_flag = ((unsigned long long)changes * 64ull <= (unsigned long long)npairs) ? 1u : 0u;
+  c = __reduce_add_sync(kFull, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(changes, c);
 }
 
 // Second tier: the pairs the walk kernel deferred, through dist_core (block per pair).

@@ -170,7 +170,7 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   unsigned dc = 0, flag = 0;
   int32_t *dlp = dl.data();
   unsigned *dcp = &dc, *fp = (shared < 0) ? &flag : nullptr;
-  if (fp) emu::launch(1, 64, 0, [&] { grsr::walk_order_kernel(pairs, npairs, fp); });
+  if (fp) emu::launch(3, 64, 0, [&] { grsr::walk_order_kernel(pairs, npairs, fp); });
   if (shared != 0) {
     size_t smem = 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * (size_t)wpb;
     emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
@@ -190,5 +190,5 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   GRSR_DISPATCH_SHAPE(t, e, emu::launch(3, (unsigned)t, smem2, [&] {
     grsr::dist_deferred_kernel<kNt, kEpt>(genomes, sp, n, pairs, dlp, dcp, out, stride);
   }));
-  return shared < 0 ? (int)flag : 0;
+  return shared < 0 ? (int)((unsigned long long)flag * 64ull <= (unsigned long long)npairs) : 0;
 }
