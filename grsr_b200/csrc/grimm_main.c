@@ -1,7 +1,7 @@
 /* grimm_main.c -- host program with GRIMM 2.01's command line for the unichromosomal path
  * (reference G/mcmain.c:195-996), calling the B200 kernels through the C ABI of include/grsr.h.
  *
- *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 2..7] [-t 1] [-v]
+ *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 1..7] [-t 1] [-v]
  *
  * What is kept byte for byte (GRSR's scr/reptA.sh:61-62,453-454 greps this text):
  *   input format          mcread_data, check_genes, delete_caps   G/mcread_input.c:83-554
@@ -16,7 +16,7 @@
  * grsr_dist_matrix, grsr_stats_matrix, grsr_scenario_batch, grsr_trial_distances); this file holds
  * no distance or scenario arithmetic.  -t 1 (print_rev_stats_t1, G/testrev.c:86-230) scores every
  * breakpoint-to-breakpoint reversal in one batched call.  Options outside the accelerated path
- * (multichromosomal mode, -c -z -t 2..4 -u -U -W -T -F -X -D -M, -S 1) are refused with a message
+ * (multichromosomal mode, -c -z -t 2..4 -u -U -W -T -F -X -D -M) are refused with a message
  * instead of being silently mis-served.
  */
 #include <ctype.h>
@@ -394,6 +394,94 @@ static int num_gpus(void)
   return k < 1 ? 1 : k;
 }
 
+/* -S 1: print_scenario (G/scenario.c:190-433), the legacy engine.  Per step the candidates are the
+ * reversals [i..j] whose two ends are breakpoints (:270-281, :313-321), i-major / j-minor; the first
+ * one whose trial permutation is closer to the destination wins (d2 < d, :343).  Every candidate's
+ * distance comes from grsr_trial_distances, a chunk of the ordered list at a time, until one
+ * succeeds.  Rows are printed with print_genes (" %4d" per gene, G/scenario.c:451-463). */
+static void print_genes_legacy(FILE *out, const int32_t *genes, int n)
+{
+  int k;
+  for (k = 0; k < n; k++) fprintf(out, " %4d", genes[k]);
+  fprintf(out, "\n");
+}
+
+static void legacy_scenario(FILE *out, const int32_t *g1, const int32_t *g2, int n, int d)
+{
+  const long chunk = 4096;
+  int32_t *cur = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)n, "current_genome");
+  int32_t *succ = (int32_t *)xmalloc(sizeof(int32_t) * (2 * (size_t)n + 1), "successors");
+  int32_t *cands = (int32_t *)xmalloc(sizeof(int32_t) * 2 * (size_t)chunk, "candidates");
+  int32_t *d2 = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)chunk, "trial distances");
+  int i, j, t = 1;
+  memcpy(cur, g1, sizeof(int32_t) * (size_t)n);
+  for (i = 0; i < 2 * n + 1; i++) succ[i] = 0;
+  for (i = 0; i + 1 < n; i++) { succ[g2[i] + n] = g2[i + 1]; succ[-g2[i + 1] + n] = -g2[i]; }
+  fprintf(out, "\n======================================================================\n\n");
+  fprintf(out, "An optimal sequence of reversals:\n");
+  fprintf(out, "Step 0: (Source)\n");
+  print_genes_legacy(out, cur, n);
+  while (d > 0) {
+    int found = 0, start = 0, end = 0, newd = d;
+    long filled = 0, c;
+    i = 0; j = -1;                                   /* cursor over the ordered candidate list */
+    for (;;) {
+      /* next candidate after (i, j) */
+      int have = 0;
+      for (; i < n; i++, j = -1) {
+        int is_start = (i == 0) ? (cur[0] != g2[0]) : (succ[cur[i - 1] + n] != cur[i]);
+        if (!is_start) continue;
+        if (j < i) j = i - 1;
+        for (j = j + 1; j < n; j++) {
+          int is_end = (j == n - 1) ? (cur[j] != g2[j]) : (succ[cur[j] + n] != cur[j + 1]);
+          if (is_end) { have = 1; break; }
+        }
+        if (have) break;
+      }
+      if (have) { cands[2 * filled] = i; cands[2 * filled + 1] = j; filled++; }
+      if (filled == chunk || (!have && filled > 0)) {
+        int rc = grsr_trial_distances(cur, g2, n, cands, filled, d2, first_device());
+        if (rc) gpu_fail(rc);
+        for (c = 0; c < filled; c++) {
+          if (d2[c] - d > 1 || d2[c] - d < -1) {     /* the reference's self-check (:323-333) */
+            int32_t *trial = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)n, "trial_genome");
+            int a = cands[2 * c], b = cands[2 * c + 1], x, y;
+            memcpy(trial, cur, sizeof(int32_t) * (size_t)n);
+            for (x = a, y = b; x <= y; x++, y--) { int32_t tmp = trial[x]; trial[x] = -trial[y]; trial[y] = -tmp; }
+            fprintf(out, "\nERROR: Potential distance caculation error:\n");
+            fprintf(out, "Source:\n\t");
+            print_genes_legacy(out, cur, n);
+            fprintf(out, "Reversal from gene %d to gene %d:\n\t", a, b);
+            print_genes_legacy(out, trial, n);
+            free(trial);
+          }
+          if (d2[c] < d) { found = 1; start = cands[2 * c]; end = cands[2 * c + 1]; newd = d2[c]; break; }
+        }
+        filled = 0;
+        if (found) break;
+      }
+      if (!have) break;
+    }
+    if (!found) {
+      fprintf(out, "ERROR: reversals ended prematurely\n");
+      break;
+    }
+    d = newd;
+    {
+      int startvalue = cur[start], endvalue = cur[end], x, y;
+      for (x = start, y = end; x <= y; x++, y--) { int32_t tmp = cur[x]; cur[x] = -cur[y]; cur[y] = -tmp; }
+      fprintf(out, "Step %d: ", t);
+      fprintf(out, "Chrom. %d, gene %d [%d] through chrom. %d, gene %d [%d]: ", 0, start, startvalue, 0, end, endvalue);
+      fprintf(out, "%s", "Reversal");
+      if (d == 0) fprintf(out, " (Destination)");
+      fprintf(out, "\n");
+      print_genes_legacy(out, cur, n);
+    }
+    t++;
+  }
+  free(cur); free(succ); free(cands); free(d2);
+}
+
 int main(int argc, char *argv[])
 {
   int c, errflg = 0, i;
@@ -582,11 +670,6 @@ int main(int argc, char *argv[])
                       "unichromosomal); use the original GRIMM\n", fn_revstats);
       die_usage(argv[0]);
     }
-    if (fn_scenario && scenario_type == 1) {
-      fprintf(stderr, "ERROR: -S 1 (the legacy scenario engine) is outside the path this build "
-                      "accelerates; use -s or -S 2..7, or the original GRIMM\n");
-      die_usage(argv[0]);
-    }
     pair[0] = gindex1; pair[1] = gindex2;
     rc = grsr_dist_pairs(in.genes, G, n, pair, 1, (int32_t *)&st, 5, first_device(), 1);
     if (rc) gpu_fail(rc);
@@ -599,7 +682,9 @@ int main(int argc, char *argv[])
     }
     if (fn_distance) fprintf(outfile, "Reversal Distance:            \t%d\n", st.d);
 
-    if (fn_scenario) {
+    if (fn_scenario && scenario_type == 1) {
+      legacy_scenario(outfile, g1, g2, n, st.d);
+    } else if (fn_scenario) {
       int max_steps = n + 1, ns = 0, k, j;
       grsr_step_t *steps = (grsr_step_t *)xmalloc(sizeof(grsr_step_t) * (size_t)max_steps, "steps");
       int32_t *cur = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)n, "current_genome");

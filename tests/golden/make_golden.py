@@ -102,6 +102,9 @@ CLI_CASES = [
     ("example_L_g32_t1_s", ["-f", "{f}", "-L", "-g", "3,2", "-t", "1", "-s"]),
     ("example_C_nog_t1", ["-f", "{f}", "-C", "-t", "1"]),
     ("example_C_t9", ["-f", "{f}", "-C", "-g", "1,2", "-t", "9"]),
+    ("example_C_g13_S1", ["-f", "{f}", "-C", "-g", "1,3", "-S", "1"]),
+    ("example_C_g12_S1_d_v", ["-f", "{f}", "-C", "-g", "1,2", "-S", "1", "-d", "-v"]),
+    ("example_L_g32_S1", ["-f", "{f}", "-L", "-g", "3,2", "-S", "1"]),
     ("nofile", ["-C"]),
     ("missingfile", ["-f", "/nonexistent/x.txt", "-C"]),
 ]
@@ -173,6 +176,10 @@ def main():
         ("hurdles_L_g21_t1", ["-f", "{hurdles}", "-L", "-g", "2,1", "-t", "1"]),
         ("hurdles_L_g13_t1", ["-f", "{hurdles}", "-L", "-g", "1,3", "-t", "1"]),
         ("n120_L_g23_t1", ["-f", "{n120}", "-L", "-g", "2,3", "-t", "1"]),
+        ("hurdles_L_g21_S1", ["-f", "{hurdles}", "-L", "-g", "2,1", "-S", "1"]),
+        ("hurdles_L_g13_S1", ["-f", "{hurdles}", "-L", "-g", "1,3", "-S", "1"]),
+        ("n120_L_g23_S1", ["-f", "{n120}", "-L", "-g", "2,3", "-S", "1"]),
+        ("n120_C_g31_S1", ["-f", "{n120}", "-C", "-g", "3,1", "-S", "1"]),
         ("messy_L", ["-f", "{messy}", "-L"]),
         ("messy_C_v", ["-f", "{messy}", "-C", "-v"]),
         ("messy_L_m", ["-f", "{messy}", "-L", "-m"]),
