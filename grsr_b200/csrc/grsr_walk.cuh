@@ -284,48 +284,56 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   // step of a walk that has ended, changes nothing, so the steps need no "am I walking" test.
   int W = 0;                                          // walks started so far (warp-uniform)
   {
-    int ci = lane - 32, myid = -1;
-    bool done = false, ended = true;
+    // Free nodes are handed out in node order from one cursor (pc) by the whole warp: 32 nodes are
+    // examined per shared-memory load, the r-th lane out of work takes the r-th free one.
+    int pc = 0, myid = -1;                            // pc: first node not examined yet (warp-uniform)
+    bool ended = true;
     unsigned x = 0xFFFFFFFFu, nx = 0xFFFFFFFFu, mn = 0, orr = 0, e = kVis;
+    uint32_t *SCR = UL;                               // 32 words of scratch (UL is not in use yet)
     for (;;) {
-      // start section: close the walk that has ended, claim the next free node of my list
+      // start section: close the walks that have ended, hand free nodes to the lanes out of work
       if (ended && myid >= 0) {
         NW[myid] = GRSR_W_MAKE(mn, MAP[nx >> shift], (orr & 1u) ? GRSR_W_ORBIT : 0u);
         myid = -1;
         x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
       }
-      const bool want = ended && !done;
-      if (want) {                                       // four list entries per round trip to shared memory
-        for (;;) {
-          const int c0 = ci + 32, c1 = ci + 64, c2 = ci + 96, c3 = ci + 128;
-          if (c0 >= K) { done = true; break; }
-          const unsigned e0 = H[((unsigned)c0 << shift) + 1];
-          const unsigned e1 = (c1 < K) ? H[((unsigned)c1 << shift) + 1] : kVis;
-          const unsigned e2 = (c2 < K) ? H[((unsigned)c2 << shift) + 1] : kVis;
-          const unsigned e3 = (c3 < K) ? H[((unsigned)c3 << shift) + 1] : kVis;
-          if (!(e0 & kVis)) { ci = c0; e = e0; break; }
-          if (!(e1 & kVis)) { ci = c1; e = e1; break; }
-          if (!(e2 & kVis)) { ci = c2; e = e2; break; }
-          if (!(e3 & kVis)) { ci = c3; e = e3; break; }
-          ci = c3;
+      const unsigned needm = __ballot_sync(kFull, ended);
+      const int myrank = __popc(needm & lt_mask);
+      int need = min(__popc(needm), kWalkMaxWalks - W), served = 0;
+      while (need > served && pc < K) {
+        const int node = pc + lane;
+        const unsigned en = (node < K) ? (unsigned)H[((unsigned)node << shift) + 1] : kVis;
+        const bool isfree = !(en & kVis);
+        const unsigned fm = __ballot_sync(kFull, isfree);
+        const int nf = __popc(fm);
+        const int take = min(need - served, nf);
+        if (take > 0) {
+          const int fr = __popc(fm & lt_mask);
+          if (isfree && fr < take) SCR[fr] = en | ((unsigned)lane << 16);
+          __syncwarp();
+          const int slot = myrank - served;
+          if (ended && slot >= 0 && slot < take) {
+            const unsigned v = SCR[slot];
+            const int mynode = pc + (int)(v >> 16);
+            e = v & 0xFFFFu;
+            myid = W + myrank;
+            x = (unsigned)mynode << shift;
+            H[x + 1] = (uint16_t)(e | kVis);
+            MAP[mynode] = (uint16_t)myid;
+            nx = e; mn = x; orr = 0; ended = false;
+          }
+          const int last = (int)(SCR[take - 1] >> 16);  // lane of the last free node handed out
+          __syncwarp();
+          pc += (nf > take) ? last + 1 : 32;
+          served += take;
+        } else {
+          pc += 32;
         }
       }
-      const bool got = want && !done;
-      const unsigned m = __ballot_sync(kFull, got);
-      if (got) {
-        myid = W + __popc(m & lt_mask);
-        if (myid < kWalkMaxWalks) {
-          x = (unsigned)ci << shift;
-          H[x + 1] = (uint16_t)(e | kVis);
-          MAP[ci] = (uint16_t)myid;
-          nx = e; mn = x; orr = 0; ended = false;
-        } else {                                      // walk table full: the leftover pass or tier 2 decides
-          myid = -1; done = true;
-        }
-      }
-      W += __popc(m);
+      W += served;
       __syncwarp();
       if (!__any_sync(kFull, !ended)) break;
+      const bool pool = (pc < K) && (W < kWalkMaxWalks);  // lanes out of work can still be served
       for (;;) {
 #pragma unroll
         for (int s = 0; s < kWalkGroup; s++) {
@@ -336,12 +344,11 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
         }
         ended = (e & kVis) != 0u;
         const unsigned walking = __ballot_sync(kFull, !ended);
-        const unsigned idle = __ballot_sync(kFull, ended && !done);
-        if (walking == 0u || __popc(idle) >= idle_min) break;
+        if (walking == 0u || (pool && 32 - __popc(walking) >= idle_min)) break;
       }
-      __syncwarp();                                   // no lane scans for a free node while others still claim
+      __syncwarp();                                   // nobody examines nodes while others still claim
     }
-    W = min(W, kWalkMaxWalks);
+    if (lane == 0) UL[0] = 0;                         // the scratch becomes the unoriented-cycle list
   }
   __syncwarp();
 
