@@ -337,7 +337,7 @@ trial_batch_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ 
   __syncthreads();
   for (long long c = blockIdx.x; c < ncand; c += gridDim.x) {
     EndsTrial<int16_t> et; et.rho0 = RHO0; et.i = cands[2 * c]; et.j = cands[2 * c + 1];
-    const Stats st = ScenSmall<NT, EPT>::template dist<false>(wk, n, et);   // walks first, see ScenSmall
+    const Stats st = dist_core<NT, EPT, false>(wk, n, et);
     if (tid == 0) out[c] = st.d;
   }
 }

@@ -63,7 +63,7 @@ step_prepare_kernel(const int32_t *__restrict__ cur, const int32_t *__restrict__
   }
   __syncthreads();
   EndsG0<int16_t> eg; eg.inv0 = INV0;
-  const Stats g0 = ScenSmall<NT, EPT>::template dist<true>(wk, n, eg);
+  const Stats g0 = dist_core<NT, EPT, true>(wk, n, eg);
   if (g0.d == 0) {
     if (tid == 0) { st->d = 0; st->h = 0; st->f = 0; st->nbp = 0; st->ncand = 0; }
     return;

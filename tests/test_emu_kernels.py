@@ -216,13 +216,3 @@ def test_emulated_scenarios_block_walks(n):
         assert status[q] == 0
         assert np.array_equal(steps[q], want)
         assert evals[q] == want_evals
-
-
-def test_emulated_trial_distances_block_walks():
-    """candidate scoring at a size where the evaluations start with the block-level walks"""
-    for n, s in ((60, 0), (60, 1), (75, 2)):
-        rng = random.Random(n * 10 + s)
-        src = gen.hurdle_rich_perm(n, n * 10 + s) if s % 2 else gen.random_signed_perm(n, rng)
-        dst = list(range(1, n + 1)) if s < 2 else gen.random_signed_perm(n, rng)
-        cands = U.breakpoint_candidates(src, dst)[:150]
-        assert np.array_equal(U.emu_trial_distances(src, dst, cands), U.orc_trial_distances(src, dst, cands))
