@@ -46,7 +46,7 @@ def _run(cmd: list[str], cwd: str | None = None) -> None:
 
 
 def cuda_sources() -> list[str]:
-    return [os.path.join(CSRC, f) for f in ("grsr_capi.cu", "grsr_core.cuh", "grsr_scenario.cuh", "grsr_stepwise.cuh", "grsr_walk.cuh", "grsr_bwalk.cuh")] + [
+    return [os.path.join(CSRC, f) for f in ("grsr_capi.cu", "grsr_core.cuh", "grsr_scenario.cuh", "grsr_stepwise.cuh", "grsr_walk.cuh")] + [
         os.path.join(ROOT, "include", "grsr.h")]
 
 

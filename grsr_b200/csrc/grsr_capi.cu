@@ -607,15 +607,6 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
 
 extern "C" {
 
-#ifdef GRSR_BW_STATS
-int grsr_debug_bw_stats(unsigned long long *out8, int reset) {
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpyFromSymbol(out8, grsr::g_bw_stats, sizeof(unsigned long long) * 8));
-  if (reset) { unsigned long long z[8] = {0}; CK(cudaMemcpyToSymbol(grsr::g_bw_stats, z, sizeof z)); }
-  return GRSR_OK;
-}
-#endif
-
 int grsr_abi_version(void) { return 1; }
 
 const char *grsr_last_error(void) { return g_err.c_str(); }

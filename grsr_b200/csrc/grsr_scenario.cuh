@@ -21,7 +21,6 @@
 // candidates are resumed from in key order, so the accepted reversal is the reference's.
 #pragma once
 #include "grsr_core.cuh"
-#include "grsr_bwalk.cuh"
 
 namespace grsr {
 
@@ -96,18 +95,8 @@ struct ScenSmall {
   typedef int16_t sval;
   typedef WorkT<uint16_t> work;
   typedef TeamBlock team;
-  // first the O(n) walks (grsr_bwalk.cuh): they settle every graph without an unoriented cycle, i.e.
-  // practically every evaluation of a hurdle-free scenario; otherwise the complete pipeline
   template <bool kKeep, class E>
-  static __device__ inline Stats dist(work &wk, int n, E e) {
-    if (bw_fits(n, NT * EPT)) {
-      bool settled;
-      const Stats st = dist_core_bwalk<NT, kKeep>(wk, n, e, settled);
-      if (settled) return st;
-      __syncthreads();
-    }
-    return dist_core<NT, EPT, kKeep>(wk, n, e);
-  }
+  static __device__ inline Stats dist(work &wk, int n, E e) { return dist_core<NT, EPT, kKeep>(wk, n, e); }
 };
 
 // Policy of the global-memory build: 32-bit ids and values; TM = one block or a whole cluster per pair.

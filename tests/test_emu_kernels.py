@@ -189,30 +189,3 @@ def test_emulated_walk_shared_rows(n, wpb):
     sq = _ordered(len(g))
     got, _ = U.emu_stats_walk(g, sq, wpb, 2, shared=1)
     assert np.array_equal(got, U.orc_stats(g, sq))
-
-
-@pytest.mark.parametrize("n", [48, 64, 97])
-def test_emulated_scenarios_block_walks(n):
-    """sizes at which the scenario kernel evaluates graphs with the block-level walks first
-    (grsr_bwalk.cuh, n >= 48) and falls back to dist_core when an unoriented cycle exists"""
-    srcs, dsts = [], []
-    for s in range(4):
-        seed = n * 100 + s
-        rng = random.Random(seed)
-        if s == 0:
-            src, dst = gen.random_signed_perm(n, rng), gen.random_signed_perm(n, rng)
-        elif s == 1:
-            src, dst = gen.hurdle_rich_perm(n, seed), list(range(1, n + 1))
-        elif s == 2:
-            src = gen.k_reversal_perm(n, rng.randrange(3, 9), rng)
-            dst = gen.k_reversal_perm(n, rng.randrange(0, 5), rng)
-        else:
-            src, dst = gen.random_signed_perm(n, rng), list(range(1, n + 1))
-        srcs.append(src)
-        dsts.append(dst)
-    steps, status, evals = U.emu_scenario(srcs, dsts, 0, 2)
-    for q in range(len(srcs)):
-        want, want_evals = U.orc_scenario(srcs[q], dsts[q])
-        assert status[q] == 0
-        assert np.array_equal(steps[q], want)
-        assert evals[q] == want_evals
