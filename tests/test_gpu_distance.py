@@ -139,3 +139,36 @@ def test_two_tier_path_exhaustive_n6(monkeypatch):
     k = len(g)
     pairs = np.array([[0, i] for i in range(1, k)] + [[i, 0] for i in range(1, k)], dtype=np.int32)
     assert np.array_equal(capi.dist_pairs(g, pairs, stats=True), U.orc_stats(g, pairs))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [700, 3000, 9000])
+def test_two_tier_path_on_degenerate_inputs(n, monkeypatch):
+    """inputs the walk kernel treats specially: identical genomes (every edge an adjacency), genomes a
+    few reversals apart (mostly adjacencies, short cycles without nodes), unsigned-like genomes (every
+    cycle unoriented: everything is deferred), in both pair orders (private / shared pi rows)"""
+    import random
+    from grsr_b200 import capi
+    rng = random.Random(n)
+    ident = list(range(1, n + 1))
+    rows = [ident, ident]
+    rows += [gen.k_reversal_perm(n, k, rng) for k in (1, 2, 5, 40, 300)]
+    pos = ident[:]
+    rng.shuffle(pos)
+    rows += [pos, [-x for x in pos], gen.random_signed_perm(n, rng)]
+    base = gen.k_reversal_perm(n, 7, rng)
+    rows += [[(base[abs(x) - 1] if x > 0 else -base[abs(x) - 1]) for x in gen.k_reversal_perm(n, k, rng)] for k in (1, 3, 9)]
+    g = np.asarray(rows, dtype=np.int32)
+    G = len(g)
+    sq = np.array([[i, j] for i in range(G) for j in range(G)], dtype=np.int32)
+    tri = np.array([[i, j] for j in range(G) for i in range(j)] * 3, dtype=np.int32)   # pi-sorted runs
+    for pairs, shared in ((sq, "0"), (tri, "1")):
+        monkeypatch.setenv("GRSR_WALK", "0")
+        one = capi.dist_pairs(g, pairs, stats=True)
+        monkeypatch.setenv("GRSR_WALK", "1")
+        monkeypatch.setenv("GRSR_WALK_SHARED", shared)      # force the private- / shared-row kernel
+        two = capi.dist_pairs(g, pairs, stats=True)
+        monkeypatch.delenv("GRSR_WALK_SHARED")
+        assert np.array_equal(two, one)
+    small = sq[:: max(1, len(sq) // 40)]
+    assert np.array_equal(capi.dist_pairs(g, small, stats=True), U.orc_stats(g, small))
