@@ -207,7 +207,7 @@ __device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
 
 // One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
 // in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
-__device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
+__device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
                                  long long p, int32_t *__restrict__ out, int stride, int shape,
                                  int32_t *defer_list, unsigned *defer_count) {
   const int shift = shape & 0xFF, idle_min = shape >> 8;   // node stride 2^shift; lanes out of work before new walks start
@@ -459,6 +459,20 @@ __device__ inline void walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     }
   }
   __syncwarp();
+  return defer != 0;
+}
+
+// A warp that had to defer every one of its first kWalkGiveUp pairs stops trying: on a batch of
+// hurdle-rich pairs the first tier then costs a few per cent instead of its full time on top of the
+// second tier's.  The rest of its pairs go to the deferred list unseen.
+static const int kWalkGiveUp = 8;
+struct WalkQuota {
+  int done, deferred;
+  __device__ inline bool gave_up() const { return done >= kWalkGiveUp && deferred == done; }
+  __device__ inline void count(bool was_deferred) { done++; deferred += was_deferred ? 1 : 0; }
+};
+__device__ inline void walk_defer_unseen(long long p, int32_t *defer_list, unsigned *defer_count) {
+  if ((threadIdx.x & 31) == 0) defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
 }
 
 // Verdict of walk_order_kernel: runs of equal pi rows are long (at most one change per 64 pairs).
@@ -491,7 +505,9 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   const long long p0 = ((long long)blockIdx.x * wpb + wid) * chunk;
   const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
   int staged = -1;
+  WalkQuota quota = {0, 0};
   for (long long p = p0; p < p1; p++) {
+    if (quota.gave_up()) { walk_defer_unseen(p, defer_list, defer_count); continue; }
     const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
     if (pj != staged) {
       const int32_t *sp = sinv + (long long)pj * n;
@@ -502,7 +518,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
       staged = pj;
       __syncwarp();
     }
-    walk_pair(wm, genomes, n, gi, p, out, stride, shape, defer_list, defer_count);
+    quota.count(walk_pair(wm, genomes, n, gi, p, out, stride, shape, defer_list, defer_count));
   }
 }
 
@@ -525,6 +541,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   walk_init_private(wm, n, lane);
   if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n + 1);
 
+  WalkQuota quota = {0, 0};
   const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
   const long long b0 = (long long)blockIdx.x * chunk;
   const long long b1 = (b0 + chunk < npairs) ? b0 + chunk : npairs;
@@ -547,8 +564,10 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
     }
     __syncthreads();
     const unsigned run = *s_end;
-    for (unsigned q = wid; q < run; q += wpb)
-      walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shape, defer_list, defer_count);
+    for (unsigned q = wid; q < run; q += wpb) {
+      if (quota.gave_up()) { walk_defer_unseen(p + q, defer_list, defer_count); continue; }
+      quota.count(walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shape, defer_list, defer_count));
+    }
     p += run;
   }
 }
