@@ -36,6 +36,7 @@
 // Results are those of dist_core, bit for bit; only which tier computes them differs.
 #pragma once
 #include "grsr_core.cuh"
+#include <type_traits>
 
 #ifdef GRSR_EMU
 #define GRSR_EMU_READ_BEFORE_WRITE_WARP() __syncwarp()
@@ -64,7 +65,8 @@ __host__ __device__ inline int walk_shift(int n) {
 // kernel argument: node stride and start threshold in one int
 __host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return shift | (idle_min << 8); }
 
-__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 3) & ~3; }   // 32-bit words of H
+// 32-bit words of H: n+2 used, padded so that 32 lanes x 16-byte loads cover it in whole rounds
+__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 127) & ~127; }
 
 // shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[256] | MAP u16[512] | misc
 __host__ __device__ inline size_t walk_tail_bytes(int n) { return (((size_t)(n + 1) * 2) + 15) & ~(size_t)15; }
@@ -251,19 +253,24 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       unsigned nl = __shfl_down_sync(kFull, L[0], 1);
       if (lane == 31) nl = nl0;
       carry = __shfl_sync(kFull, R[7], 31);
+      // the chunk's genes; a chunk that lies wholly inside the row has no sentinel genes to mask
+      auto genes = [&](auto all_real) {
+        constexpr bool kAllReal = decltype(all_real)::value;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const unsigned Lt = L[k], Rt = R[k];
-        const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
-        const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
-        const bool real = (tb + k < n);
-        const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
-        nadj += (adjL && real) ? 1u : 0u;
-        const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
-        const bool fwd = Lt < Rt;                                     // L_t = 2p+1: its entry is the low half
-        const unsigned word = walk_pack(fwd ? ea : eb, fwd ? eb : ea);
-        if (real) *(uint32_t *)((char *)Hw + Lt + Rt + 1u) = word;    // L_t + R_t + 1 = 4(p+1): word p+1
-      }
+        for (int k = 0; k < 8; k++) {
+          const unsigned Lt = L[k], Rt = R[k];
+          const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
+          const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
+          const bool real = kAllReal || (tb + k < n);
+          const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
+          nadj += (adjL && real) ? 1u : 0u;
+          const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
+          const bool fwd = Lt < Rt;                                     // L_t = 2p+1: its entry is the low half
+          const unsigned word = walk_pack(fwd ? ea : eb, fwd ? eb : ea);
+          if (real) *(uint32_t *)((char *)Hw + Lt + Rt + 1u) = word;    // L_t + R_t + 1 = 4(p+1): word p+1
+        }
+      };
+      if (cb + 256 <= n) genes(std::true_type()); else genes(std::false_type());
 #pragma unroll
       for (int k = 0; k < 8; k++) G[k] = Gn[k];
     }
@@ -367,11 +374,8 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     __syncwarp();
     const uint4 *H4 = (const uint4 *)Hw;
     const int hq = hwords >> 2;
-    for (int q0 = 0; q0 < hq; q0 += 32) {
-      const int q = q0 + lane;
-      uint4 x;
-      x.x = x.y = x.z = x.w = 0x80008000u;
-      if (q < hq) x = H4[q];
+    for (int q = lane; q < hq; q += 32) {                // hq is a multiple of 32: whole rounds
+      const uint4 x = H4[q];
       const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
       if (__any_sync(kFull, some)) {
         if (some) {
