@@ -433,10 +433,16 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     for (unsigned k = 0; k < nun && !defer; k++) {
       const unsigned qq = UL[1 + k];
       bool hit = false;
-      for (int it = 0; it < 8; it++) {
-        const unsigned v = qq + 2u + 32u * it + lane;
+      // the first vertices right of q nearly always decide (q sits inside a long oriented cycle):
+      // 4 of them first, then 32 at a time, 260 in all
+      unsigned off = 0;
+      for (int it = 0; it < 9; it++) {
+        const unsigned width = (it == 0) ? 4u : 32u;
+        const unsigned v = qq + 2u + off + lane;
+        off += width;
         int st = 2;                                   // past the last vertex: stop
-        if (v < (unsigned)S) {
+        if ((unsigned)lane >= width) st = 0;          // not probing in this round
+        else if (v < (unsigned)S) {
           st = 0;
           const unsigned ent = H[v + 1];
           if ((ent & 0x7FFFu) != v) {                 // not an adjacency end
