@@ -47,10 +47,10 @@
 namespace grsr {
 
 static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a walk (or an adjacency end)
-static const int kWalkMaxNodes = 512;        // nodes (possible walk starts) per pair
+static const int kWalkMaxNodes = 256;        // nodes (possible walk starts) per pair
 static const int kWalkMaxWalks = 256;        // walks per pair (8 words per lane in the jumping phase)
-static const int kWalkGroup = 4;             // tau steps between two votes
-static const int kWalkIdle = 12;             // default: lanes that must be out of work before new walks start
+static const int kWalkGroup = 8;             // tau steps between two votes
+static const int kWalkIdle = 8;              // default: lanes that must be out of work before new walks start
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
 static const int kWalkLeftoverBudget = 1536; // steps a lane may spend on orbits without a node
 
@@ -68,7 +68,7 @@ __host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return 
 // 32-bit words of H: n+2 used, padded so that 32 lanes x 16-byte loads cover it in whole rounds
 __host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 127) & ~127; }
 
-// shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[256] | MAP u16[512] | misc
+// shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[256] | MAP u16[256] | misc
 __host__ __device__ inline size_t walk_tail_bytes(int n) { return (((size_t)(n + 1) * 2) + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t walk_warp_bytes(int n) {
   size_t b = walk_tail_bytes(n);
