@@ -1,23 +1,37 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the reversal-distance hot path on the workload BASELINE.json quotes:
-config 3 = all 499,500 pairs of 1000 synthetic genomes x 2000 signed blocks (seed 7).
+"""bench.py -- throughput of the GRIMM reversal-distance / scenario hot path on the workloads
+BASELINE.json quotes.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One step = one pass of the path over the whole pair list (at N > 1 each rank owns a contiguous
-1/N slice of the upper triangle; no collective on the data path; strong scaling of a fixed job).
+Headline (metric / value / e2e / roofline / cpu_baseline), config 3: all 499,500 pairs of 1000
+synthetic genomes x 2000 signed blocks (seed 7).  One step = one pass of the distance path over the
+whole pair list (at N > 1 each rank owns a contiguous 1/N slice of the upper triangle; no collective
+on the data path; strong scaling of a fixed job).
 
-  value          pairs/s, kernel only, inputs resident in HBM, per-step CUDA events on the launch
+  value          pairs/s, kernels only, inputs resident in HBM, per-step CUDA events on the launch
                  stream, L2 flushed between steps, max over ranks
-  e2e            pairs/s through the C ABI call a GRIMM binding makes (grsr_dist_matrix_shard) with
-                 HOST buffers: H2D of the genome table, signed inverses, pair generation, kernel,
-                 D2H of the distances all inside the timed region
+  e2e            pairs/s through the call a GRIMM binding makes -- grsr_dist_matrix(genomes, G, n,
+                 distmatrix, first_device 0, ngpus N), ONE process, HOST buffers in, the finished
+                 G x G matrix out (INTEGRATION.md section 2.1 replaces setinvmatrix by it) -- with the
+                 H2D of the genome table, validation, signed inverses, pair generation, kernels and
+                 the D2H of the matrix inside the timed region.  At N > 1 rank 0 makes that call on all
+                 N devices while the other ranks wait on the CPU; the one-process-per-GPU shard call
+                 (grsr_dist_matrix_shard) is timed beside it as e2e_multiprocess.
   roofline       algorithmic bytes (8n+4 per pair) / kernel time vs the
                  measured HBM peak of MEASURED_PEAKS.json
   cpu_baseline   the UNMODIFIED reference (oracle/_ref/libgrimmref.so) on all host cores, on a
-                 bounded sample of the same pair list (rank 0, N = 1 only)
+                 bounded sample of the same pair list (rank 0, N = 1 only); at every N the GPU
+                 matrix is compared with the reference on a sample spread over all ranks' slices
 
---impl reference times that reference CPU implementation alone (same metric / config keys).
+Secondary legs in the same JSON line ("scenario", run by rank 0 in-process on all N devices):
+  config4        BASELINE.json config 4: 10,000 hurdle/fortress-rich pairs x 5000 blocks, the first
+                 CONFIG4_STEP_CAP steps of every pair's -s scenario (the whole scenarios are hours
+                 on any hardware), sharded over the N devices by the library's cross-device queue
+  config5        (N = 1) one pair, n = 100,000: time to first step, steps/s over a 2000-step prefix
+  cli            (N = 1) wall time of bin/grimm vs the reference binary on configs 1 and 2
+
+--impl reference times the reference CPU implementation of the headline alone (same metric/config).
 """
 from __future__ import annotations
 
@@ -41,7 +55,18 @@ G_CFG, N_CFG, SEED_CFG = 1000, 2000, 7
 METRIC = "reversal_distance_pairs_per_sec"
 UNIT = "pairs/s"
 BYTES_PER_PAIR = 8 * N_CFG + 4          # read pi and gamma as int32, write one int32 distance
+CONFIG4_PAIRS, CONFIG4_GENES, CONFIG4_STEP_CAP = 10000, 5000, 8
+CONFIG5_GENES, CONFIG5_SEED, CONFIG5_PREFIX = 100000, 5, 2000
 I32P = ctypes.POINTER(ctypes.c_int)
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "grimm")
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
 def workload_config(extra=None):
@@ -57,7 +82,6 @@ def workload_config(extra=None):
 
 
 def make_genomes():
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     g = gen.random_genomes(G_CFG, N_CFG, SEED_CFG)
     # -C: align every genome on the first gene of genome 1 (host preprocessing of the CLI,
     # reference G/circ_align.c:50); genome 1 is the identity so this is a rotation / flip per row
@@ -78,9 +102,8 @@ def make_genomes():
 def load_cpu_reference():
     """(kind, callable(genomes, pairs, threads) -> distances).  Prefers the unmodified reference
     compiled in place; falls back to the oracle port (single thread per process)."""
-    ref = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")
-    if os.path.exists(ref):
-        lib = ctypes.CDLL(ref)
+    if os.path.exists(REF_LIB):
+        lib = ctypes.CDLL(REF_LIB)
 
         def run(genomes, pairs, threads):
             out = np.zeros(len(pairs), dtype=np.int32)
@@ -111,6 +134,11 @@ def load_cpu_reference():
     return "port", run1
 
 
+def triangle_pairs(G):
+    j, i = np.tril_indices(G, k=-1)
+    return np.stack([i, j], axis=1).astype(np.int32)   # column-by-column triangle, as the GPU arm
+
+
 def cpu_sample_rate(genomes, pairs, seconds: float):
     """Time the CPU reference on a bounded prefix of the pair list sized for about `seconds`."""
     kind, run = load_cpu_reference()
@@ -134,8 +162,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     genomes = make_genomes()
-    j, i = np.tril_indices(G_CFG, k=-1)
-    pairs = np.stack([i, j], axis=1).astype(np.int32)   # column-by-column triangle, as the GPU arm
+    pairs = triangle_pairs(G_CFG)
     kind, run = load_cpu_reference()
     cores = os.cpu_count() or 1
     # size one step for a few seconds so that steps+warmup stay within minutes
@@ -236,14 +263,21 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py needs a CUDA device: the path has no CPU implementation")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group(backend="nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")     # waits that must not occupy the GPUs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -257,7 +291,7 @@ def run_gpu_arm(args):
     lo, hi = P * rank // world, P * (rank + 1) // world
     cnt = hi - lo
 
-    # resident inputs
+    # ---- value: resident inputs, kernels only -------------------------------------------------------
     stream = torch.cuda.current_stream().cuda_stream
     d_gen = torch.from_numpy(genomes).to(dev)
     d_sinv = torch.empty_like(d_gen)
@@ -268,10 +302,12 @@ def run_gpu_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_dev():
-        capi.dist_pairs_dev(d_gen.data_ptr(), d_sinv.data_ptr(), N_CFG, d_pairs.data_ptr(), cnt,
-                            d_out.data_ptr(), 1, stream)
+        capi.dist_pairs_sorted_dev(d_gen.data_ptr(), d_sinv.data_ptr(), N_CFG, d_pairs.data_ptr(), cnt,
+                                   d_out.data_ptr(), 1, stream)
+    launches_per_step = 2       # dist_walk_shared_kernel + dist_deferred_kernel (the scratch memset is not ours)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_dev()
     barrier()
     sampler = ClockSampler(local)
@@ -291,32 +327,45 @@ def run_gpu_arm(args):
     total_ms = max_over_ranks(float(sum(ms)))
     kernel_ms = float(np.mean(ms))
     value = P * args.steps / (total_ms / 1e3)
+    resident = d_out.cpu().numpy()
 
-    # end to end through the host-buffer C ABI
+    # ---- e2e, one process per GPU: the shard call with host buffers ----------------------------------
     h_gen = torch.from_numpy(genomes).pin_memory()
+    g_np = h_gen.numpy()
     h_out = torch.empty((cnt,), dtype=torch.int32).pin_memory()
-    g_np, o_np = h_gen.numpy(), h_out.numpy()
-    for _ in range(max(args.warmup, 3)):
+    o_np = h_out.numpy()
+    for _ in range(warm):
         capi.dist_matrix_shard(g_np, rank, world, device=local, out=o_np)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         capi.dist_matrix_shard(g_np, rank, world, device=local, out=o_np)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
+    mp_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop(t_region0, t_region1) if rank == 0 else None
-    # the two paths must agree before any number is reported
-    if not np.array_equal(o_np, d_out.cpu().numpy()):
+    if not np.array_equal(o_np, resident):
         raise SystemExit("device-resident and host-buffer paths disagree")
-    e2e_value = P * args.steps / e2e_s
+    cpu_barrier()
 
+    # ---- e2e, the bound call: rank 0 alone, grsr_dist_matrix on all N devices ---------------------------
+    line = None
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-        else:
-            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        h_mat = torch.empty((G_CFG, G_CFG), dtype=torch.int32).pin_memory()
+        m_np = h_mat.numpy()
+        for _ in range(warm):
+            capi.dist_matrix(g_np, first_device=0, ngpus=world, out=m_np)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            capi.dist_matrix(g_np, first_device=0, ngpus=world, out=m_np)
+        e2e_s = time.perf_counter() - t0
+        pairs = triangle_pairs(G_CFG)
+        if not np.array_equal(m_np[pairs[lo:hi, 0], pairs[lo:hi, 1]], resident):
+            raise SystemExit("grsr_dist_matrix and the device-resident path disagree")
+        if not (np.array_equal(m_np, m_np.T) and not m_np.diagonal().any()):
+            raise SystemExit("grsr_dist_matrix: matrix not symmetric with zero diagonal")
+        flat = m_np[pairs[:, 0], pairs[:, 1]]
+
+        peak, peak_src = hbm_peak()
         achieved = cnt * BYTES_PER_PAIR / (kernel_ms / 1e3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "dist_kernel_traffic.json")
@@ -324,144 +373,200 @@ def run_gpu_arm(args):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic,
-                    "kernel": "grsr::dist_walk_shared_kernel (+ walk_order_kernel, dist_deferred_kernel on the deferred pairs)",
+                    "kernel": "grsr::dist_walk_shared_kernel (+ dist_deferred_kernel on the deferred pairs)",
                     "kernel_ms": kernel_ms,
                     "algorithmic_bytes_per_pair": BYTES_PER_PAIR, "pairs_per_launch": cnt, "peak_source": peak_src}
         cpu = None
-        if world == 1 and not args.no_cpu:
-            pairs = capi.triangle_pairs(G_CFG)          # same flat order as the GPU result
-            cpu, d_cpu, sample = cpu_sample_rate(genomes, pairs, seconds=12.0)
-            if not np.array_equal(d_cpu, o_np[:len(sample)]):
-                raise SystemExit("GPU distances differ from the CPU reference on the baseline sample")
-            cpu["checked"] = "GPU distances equal the CPU reference on all %d sample pairs" % len(sample)
-        scen = scenario_leg(capi) if (world == 1 and not args.no_cpu and not args.no_scenario) else None
+        if not args.no_cpu:
+            if world == 1:
+                cpu, d_cpu, sample = cpu_sample_rate(genomes, pairs, seconds=12.0)
+                if not np.array_equal(d_cpu, flat[:len(sample)]):
+                    raise SystemExit("GPU distances differ from the CPU reference on the baseline sample")
+                cpu["checked"] = "GPU distances equal the CPU reference on all %d sample pairs" % len(sample)
+            else:
+                # every rank's slice is covered: a strided sample of the whole list against the reference
+                kind, run = load_cpu_reference()
+                idx = np.arange(0, P, max(1, P // 16384))
+                d_cpu = run(genomes, np.ascontiguousarray(pairs[idx]), os.cpu_count() or 1)
+                if not np.array_equal(d_cpu, flat[idx]):
+                    raise SystemExit("GPU distances differ from the CPU reference on the cross-rank sample")
+                cpu = {"checked": "grsr_dist_matrix(ngpus=%d) equals the CPU %s on %d pairs spread over all "
+                                  "%d slices (the timed baseline is reported at N = 1 only)" % (world, kind, len(idx), world)}
+        scen = None
+        if not args.no_scenario:
+            scen = {"config4": config4_leg(capi, world, no_cpu=args.no_cpu)}
+            if world == 1 and not args.no_cpu:
+                scen["config5"] = config5_leg(capi)
+                scen["cli"] = cli_leg()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": workload_config({"l2": "flushed between timed steps with a 256 MiB write; per-step CUDA events",
                                        "threads_per_block": os.environ.get("GRSR_THREADS", "auto")}),
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(genomes.nbytes) * world,
-                    "d2h_bytes_per_step": int(P * 4), "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "grsr_dist_matrix_shard (host buffers, pinned)"},
-            "gpu_launches": 4 * args.steps * world, "clocks": clocks, "scenario": scen,
+            "e2e": {"value": P * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(genomes.nbytes) * world,
+                    "d2h_bytes_per_step": int(G_CFG * G_CFG * 4), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "grsr_dist_matrix(genomes, %d, %d, distmatrix, 0, %d): one process, pinned host buffers, "
+                           "full G x G matrix out" % (G_CFG, N_CFG, world)},
+            "e2e_multiprocess": {"value": P * args.steps / mp_s, "unit": UNIT, "ms_per_step": mp_s / args.steps * 1e3,
+                                 "h2d_bytes_per_step": int(genomes.nbytes) * world, "d2h_bytes_per_step": int(P * 4),
+                                 "api": "grsr_dist_matrix_shard, one process per GPU (max over ranks)"},
+            "gpu_launches": launches_per_step * args.steps * world, "clocks": clocks, "scenario": scen,
         }
+    cpu_barrier()
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-# ---- scenario leg (secondary metric of BASELINE.json: scenario reversals/s) ---------------------------
+# ---- scenario legs (secondary metric of BASELINE.json: scenario reversals/s) ---------------------------
 
-def _ref_scenario_worker(args):
-    """One reference scenario in a worker process (the reference prints through a global FILE*)."""
-    src, dst = args
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so"))
-    n = len(src)
-    steps = np.zeros(2 * (n + 2), dtype=np.int32)
-    k = lib.ref_scenario(src.ctypes.data_as(I32P), dst.ctypes.data_as(I32P), n, steps.ctypes.data_as(I32P), n + 2)
+def _hurdle_rows(seeds):
+    return [gen.hurdle_rich_perm(CONFIG4_GENES, s) for s in seeds]
+
+
+def config4_sources(k):
+    """gen.hurdle_rich_perm(5000, pair_index) for pair_index < k, built on all host cores."""
+    from concurrent.futures import ProcessPoolExecutor
+    cores = os.cpu_count() or 1
+    chunks = [list(range(s, min(k, s + 64))) for s in range(0, k, 64)]
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        rows = [r for part in ex.map(_hurdle_rows, chunks) for r in part]
+    return np.array(rows, dtype=np.int32)
+
+
+def _ref_prefix_worker(args):
+    """The first `cap` steps of one reference scenario (the reference prints through a global FILE*;
+    ref_scenario_prefix runs print_scenario_2 in a forked child and stops it after `cap` steps)."""
+    src, dst, cap = args
+    lib = ctypes.CDLL(REF_LIB)
+    steps = np.zeros(2 * max(cap, 1), dtype=np.int32)
+    k = lib.ref_scenario_prefix(src.ctypes.data_as(I32P), dst.ctypes.data_as(I32P), len(src),
+                                steps.ctypes.data_as(I32P), cap)
     return steps[:2 * max(k, 0)].reshape(-1, 2)
 
 
-def scenario_leg(capi):
-    """Reversals/s of grsr_scenario_batch (host buffers in, step lists out) on two bounded samples:
-    config-4-sized random pairs, and hurdle/fortress-rich pairs (where the reference brute-forces
-    every breakpoint pair); the latter is also timed on the reference CPU and compared step by step."""
-    import random
+def config4_leg(capi, ngpus, no_cpu=False):
+    """Config 4 at its stated shape: 10,000 (source, identity) pairs of 5000 blocks, source =
+    gen.hurdle_rich_perm(5000, pair index); the first CONFIG4_STEP_CAP steps of every scenario through
+    grsr_scenario_prefix on `ngpus` devices (one process; the library's cross-device pair queue)."""
     from concurrent.futures import ProcessPoolExecutor
-    out = {}
-    rng = random.Random(4)
-    n, k = 5000, 148
-    src = np.array([gen.random_signed_perm(n, rng) for _ in range(k)], dtype=np.int32)
+    n, k, cap = CONFIG4_GENES, CONFIG4_PAIRS, CONFIG4_STEP_CAP
+    src = config4_sources(k)
     dst = np.tile(np.arange(1, n + 1, dtype=np.int32), (k, 1))
-    capi.scenario_batch(src[:2], dst[:2])
+    capi.scenario_prefix(src[:64 * ngpus], dst[:64 * ngpus], 1, ngpus=ngpus)       # warm-up: contexts, buffers
     t0 = time.perf_counter()
-    steps = capi.scenario_batch(src, dst)
+    steps, done, evals = capi.scenario_prefix(src, dst, cap, ngpus=ngpus)
     dt = time.perf_counter() - t0
-    tot = sum(len(x) for x in steps)
-    out["random_n5000"] = {"pairs": k, "genes": n, "reversals": tot, "seconds": dt, "value": tot / dt,
-                           "unit": "reversals/s", "roofline_frac_hbm": tot / dt * (12 * n + 16) / 6554.6e9}
-    n, k = 300, 2368
-    src = np.array([gen.hurdle_rich_perm(n, 9000 + s) for s in range(k)], dtype=np.int32)
-    dst = np.tile(np.arange(1, n + 1, dtype=np.int32), (k, 1))
-    t0 = time.perf_counter()
-    steps = capi.scenario_batch(src, dst)
-    dt = time.perf_counter() - t0
-    tot = sum(len(x) for x in steps)
-    leg = {"pairs": k, "genes": n, "reversals": tot, "seconds": dt, "value": tot / dt, "unit": "reversals/s"}
-    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")):
+    tot = int(sum(len(x) for x in steps))
+    peak, _ = hbm_peak()
+    leg = {"workload": "config4: %d hurdle/fortress-rich pairs x %d blocks (gen.hurdle_rich_perm(5000, pair index) -> "
+                       "identity), -s scenario, first %d steps of every pair" % (k, n, cap),
+           "pairs": k, "genes": n, "step_cap": cap, "n_gpus": ngpus, "reversals": tot, "seconds": dt,
+           "value": tot / dt, "unit": "reversals/s",
+           "full_evaluations": int(evals.sum()), "evaluations_per_s": float(evals.sum()) / dt,
+           "api": "grsr_scenario_prefix (host buffers in, step lists out, one process, ngpus=%d)" % ngpus,
+           "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peak,
+                        "achieved": tot / dt * (12 * n + 16) / 1e9, "frac": tot / dt * (12 * n + 16) / 1e9 / peak,
+                        "algorithmic_bytes_per_step": 12 * n + 16,
+                        "achieved_per_evaluation_bytes": float(evals.sum()) / dt * 8 * n / 1e9}}
+    if not no_cpu and os.path.exists(REF_LIB):
         cores = os.cpu_count() or 1
-        m = min(k, 2 * cores)
+        m = min(k, cores)
+        idx = [int(q) for q in np.linspace(0, k - 1, m)]          # pairs spread over the whole batch
         t0 = time.perf_counter()
         with ProcessPoolExecutor(max_workers=cores) as ex:
-            ref = list(ex.map(_ref_scenario_worker, [(src[q], dst[q]) for q in range(m)]))
+            ref = list(ex.map(_ref_prefix_worker, [(src[q], dst[q], cap) for q in idx]))
         rdt = time.perf_counter() - t0
-        if not all(np.array_equal(a, b) for a, b in zip(ref, steps[:m])):
-            raise SystemExit("GPU scenarios differ from the CPU reference on the scenario sample")
+        if not all(np.array_equal(a, steps[q]) for a, q in zip(ref, idx)):
+            raise SystemExit("GPU scenario prefixes differ from the CPU reference on the config-4 sample")
         rtot = sum(len(x) for x in ref)
         leg["cpu_baseline"] = {"value": rtot / rdt, "unit": "reversals/s", "cores": cores, "kind": "reference",
-                               "sample": "first %d pairs, one process per pair on %d cores, %.1f s; step lists equal"
-                                         % (m, cores, rdt)}
-    out["hurdle_rich_n300"] = leg
-    # one hurdle-rich pair alone (the command-line case): the library scores each step's candidates
-    # across the whole GPU (grsr_stepwise.cuh) instead of one after another inside one block
-    n = 300
-    one_src = np.array(gen.hurdle_rich_perm(n, 1), dtype=np.int32)
-    one_dst = np.arange(1, n + 1, dtype=np.int32)
-    capi.scenario_batch(one_src, one_dst)
+                               "sample": "%d pairs spread over the batch, first %d steps each, one reference process "
+                                         "per pair on %d cores, %.1f s; step lists equal the GPU's" % (m, cap, cores, rdt)}
+    return leg
+
+
+def config5_leg(capi):
+    """Config 5: one pair, n = 100,000 random signed (seed 5) -> identity, one GPU (a single scenario
+    is a chain of steps: replicas only).  Time to first step and steps/s over a fixed prefix; the
+    prefix is compared with the reference's (tests/golden/scenario_prefixes.npz)."""
+    import random
+    n = CONFIG5_GENES
+    src = np.array(gen.random_signed_perm(n, random.Random(CONFIG5_SEED)), dtype=np.int32)
+    dst = np.arange(1, n + 1, dtype=np.int32)
+    capi.scenario_prefix(src, dst, 1)
     t0 = time.perf_counter()
-    one = capi.scenario_batch(one_src, one_dst)[0]
-    dt = time.perf_counter() - t0
-    leg = {"pairs": 1, "genes": n, "reversals": len(one), "seconds": dt, "value": len(one) / dt,
-           "unit": "reversals/s"}
-    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")):
-        t0 = time.perf_counter()
-        ref1 = _ref_scenario_worker((one_src, one_dst))
-        rdt = time.perf_counter() - t0
-        if not np.array_equal(ref1, one):
-            raise SystemExit("GPU scenario differs from the CPU reference on the single-pair sample")
-        leg["cpu_baseline"] = {"value": len(ref1) / rdt, "unit": "reversals/s", "cores": 1, "kind": "reference",
-                               "sample": "the same pair, one process, %.2f s; step lists equal" % rdt}
-    out["single_hurdle_rich_pair_n300"] = leg
-    # config-4 size: the unit of work of a hurdle-rich scenario is one full distance evaluation of
-    # a trial permutation (the reference makes ~1e7 of them per pair at n = 5000); score 16384
-    # candidate reversals of one hurdle-rich pair in one call and compare a sample with the reference
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    n = 5000
-    src5 = np.array(gen.hurdle_rich_perm(n, 4), dtype=np.int32)
-    dst5 = np.arange(1, n + 1, dtype=np.int32)
-    rng = np.random.default_rng(4)
-    ci = rng.integers(0, n, size=16384)
-    cj = rng.integers(0, n, size=16384)
-    cands = np.stack([np.minimum(ci, cj), np.maximum(ci, cj)], axis=1).astype(np.int32)
-    capi.trial_distances(src5, dst5, cands[:64])
+    capi.scenario_prefix(src, dst, 1)
+    first = time.perf_counter() - t0
     t0 = time.perf_counter()
-    d2 = capi.trial_distances(src5, dst5, cands)
+    steps, done, _ = capi.scenario_prefix(src, dst, CONFIG5_PREFIX)
     dt = time.perf_counter() - t0
-    leg = {"candidates": len(cands), "genes": n, "seconds": dt, "value": len(cands) / dt,
-           "unit": "evaluations/s", "roofline_frac_hbm": len(cands) / dt * 8 * n / 6554.6e9}
-    ref = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")
-    if os.path.exists(ref):
-        lib = ctypes.CDLL(ref)
-        cores = os.cpu_count() or 1
-        m = 64 * cores
-        trials = np.tile(src5, (m, 1))
-        for q in range(m):
-            i, j = cands[q]
-            trials[q, i:j + 1] = -src5[i:j + 1][::-1]
-        table = np.ascontiguousarray(np.vstack([trials, dst5[None, :]]), dtype=np.int32)
-        prs = np.stack([np.arange(m), np.full(m, m)], axis=1).astype(np.int32)   # gamma = trial, pi = dest
-        outr = np.zeros(m, dtype=np.int32)
-        t0 = time.perf_counter()
-        lib.ref_dist_pairs(table.ctypes.data_as(I32P), n, prs.ctypes.data_as(I32P), ctypes.c_long(m),
-                           outr.ctypes.data_as(I32P), 1, cores)
-        rdt = time.perf_counter() - t0
-        if not np.array_equal(outr, d2[:m]):
-            raise SystemExit("GPU trial distances differ from the CPU reference")
-        leg["cpu_baseline"] = {"value": m / rdt, "unit": "evaluations/s", "cores": cores, "kind": "reference",
-                               "sample": "first %d candidates on %d host threads, %.3f s; distances equal" % (m, cores, rdt)}
-    out["trial_evaluations_n5000"] = leg
+    peak, _ = hbm_peak()
+    leg = {"workload": "config5: one pair, %d blocks, random signed seed %d -> identity, first %d steps" % (n, CONFIG5_SEED, CONFIG5_PREFIX),
+           "genes": n, "steps": len(steps[0]), "seconds": dt, "value": len(steps[0]) / dt, "unit": "reversals/s",
+           "time_to_first_step_s": first,
+           "roofline_frac_hbm": len(steps[0]) / dt * (12 * n + 16) / 1e9 / peak}
+    fx = os.path.join(ROOT, "tests", "golden", "scenario_prefixes.npz")
+    if os.path.exists(fx):
+        want = np.load(fx)["cfg5_steps"][:CONFIG5_PREFIX]
+        if not np.array_equal(steps[0][:len(want)], want):
+            raise SystemExit("config 5: GPU step prefix differs from the reference fixture")
+        leg["checked"] = "first %d steps equal the reference's (tests/golden/scenario_prefixes.npz)" % len(want)
+    return leg
+
+
+def cli_leg():
+    """Drop-in latency where GRSR uses it (scr/reptA.sh:61 starts one grimm per genome pair): wall time
+    of the host program against the reference binary, process start-up included."""
+    from grsr_b200 import build
+    ours = build.CLI
+    if not os.path.exists(ours):
+        return {"unavailable": "grsr_b200/bin/grimm not built"}
+    ex = os.path.join(ROOT, "tests", "golden", "example_mgr_macro.txt")
+    tmp = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(tmp, exist_ok=True)
+    cfg2 = os.path.join(tmp, "bench_config2.txt")
+    g2 = gen.random_genomes(25, 500, 1)
+    with open(cfg2, "w") as f:
+        for k, row in enumerate(g2):
+            f.write(">g%d\n%s $\n" % (k + 1, " ".join(str(int(x)) for x in row)))
+
+    def wall(binary, argv, reps):
+        best, out = None, None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = subprocess.run([binary] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None, r.stderr.decode()[-200:]
+            best = dt if best is None else min(best, dt)
+            out = r.stdout.decode()
+        return best, out
+
+    def strip(text):
+        return "\n".join(ln for ln in text.splitlines() if not ln.startswith(("Running:", "Input:")))
+
+    out = {}
+    for name, argv in (("config1_scenario_pair_1_2", ["-f", ex, "-C", "-g", "1,2"]),
+                       ("config1_matrix", ["-f", ex, "-C", "-m"]),
+                       ("config2_matrix_25x500", ["-f", cfg2, "-C", "-m"])):
+        t_ours, o_ours = wall(ours, argv, 5)
+        leg = {"argv": " ".join(argv[2:]), "grsr_wall_s": t_ours}
+        if os.path.exists(REF_BIN):
+            t_ref, o_ref = wall(REF_BIN, argv, 5)
+            leg["reference_wall_s"] = t_ref
+            if t_ours is not None and t_ref is not None:
+                leg["same_output"] = strip(o_ours) == strip(o_ref)
+        out[name] = leg
+    # start-up alone: the cheapest command that creates the CUDA context (a 2-genome, 3-gene matrix)
+    tiny = os.path.join(tmp, "bench_tiny.txt")
+    with open(tiny, "w") as f:
+        f.write(">a\n1 2 3 $\n>b\n1 -2 3 $\n")
+    t_ours, _ = wall(ours, ["-f", tiny, "-L", "-d", "-g", "1,2"], 5)
+    out["process_startup_s"] = t_ours
     return out
 
 
@@ -471,8 +576,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="grsr", choices=["grsr", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and scenario legs")
-    ap.add_argument("--no-scenario", action="store_true", help="skip the scenario leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-reference legs (cpu_baseline, config5, cli)")
+    ap.add_argument("--no-scenario", action="store_true", help="skip the scenario legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

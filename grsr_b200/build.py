@@ -58,6 +58,15 @@ def build_cuda(force: bool = False) -> str:
     return LIB
 
 
+def build_cuda_profile(force: bool = False) -> str:
+    """Diagnostic twin of the library with per-phase cycle counters compiled in (scripts/prof_phases.py)."""
+    out = os.path.join(LIBDIR, "libgrsr_cuda_prof.so")
+    os.makedirs(LIBDIR, exist_ok=True)
+    if force or not _newer(out, cuda_sources()):
+        _run([_nvcc(), *NVCC_FLAGS, "-DGRSR_PHASE_PROFILE", "-o", out, os.path.join(CSRC, "grsr_capi.cu")])
+    return out
+
+
 def cli_sources() -> list[str]:
     return [os.path.join(CSRC, f) for f in ("grimm_main.c",)] + [os.path.join(ROOT, "include", "grsr.h")]
 

@@ -42,11 +42,15 @@ SIGNATURES = {
     "grsr_stats_matrix": (ctypes.c_int, [I32P, ctypes.c_int, ctypes.c_int, I32P, ctypes.c_int, ctypes.c_int]),
     "grsr_scenario_batch": (ctypes.c_int, [I32P, I32P, ctypes.c_int, ctypes.c_int, I32P, I32P, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_int]),
+    "grsr_scenario_prefix": (ctypes.c_int, [I32P, I32P, ctypes.c_int, ctypes.c_int, I32P, I32P, ctypes.c_int,
+                                            I32P, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_int]),
     "grsr_trial_distances": (ctypes.c_int, [I32P, I32P, ctypes.c_int, I32P, ctypes.c_int64, I32P, ctypes.c_int]),
     "grsr_signed_inverse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
     "grsr_dist_pairs_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "grsr_dist_pairs_sorted_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                  ctypes.c_int64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "grsr_triangle_pairs_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                                ctypes.c_void_p]),
 }
@@ -55,7 +59,7 @@ SIGNATURES = {
 def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("GRSR_LIB", _build.LIB)      # diagnostic builds (scripts/prof_phases.py)
         if not os.path.exists(path):
             raise GrsrError(ERR_NODEVICE, f"{path} is not built (run python -m grsr_b200.build); "
                                           "there is no CPU implementation to fall back to")
@@ -162,6 +166,23 @@ def scenario_batch(src, dst, first_device: int = 0, ngpus: int = 1) -> list[np.n
     return [steps[p, :ns[p]].copy() for p in range(npairs)]
 
 
+def scenario_prefix(src, dst, max_steps: int, first_device: int = 0, ngpus: int = 1):
+    """The first max_steps reversals of every scenario: (step lists, complete flags, evaluations)."""
+    s = _i32(src)
+    d = _i32(dst)
+    if s.ndim == 1:
+        s = s[None, :]
+        d = d[None, :]
+    npairs, n = s.shape
+    steps = np.zeros((npairs, max(max_steps, 1), 2), dtype=np.int32)
+    ns = np.zeros(npairs, dtype=np.int32)
+    done = np.zeros(npairs, dtype=np.int32)
+    ev = np.zeros(npairs, dtype=np.int64)
+    _check(lib().grsr_scenario_prefix(_p(s), _p(d), npairs, n, _p(steps), _p(ns), max_steps, _p(done),
+                                      ev.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), first_device, ngpus))
+    return [steps[p, :ns[p]].copy() for p in range(npairs)], done.astype(bool), ev
+
+
 def trial_distances(src, dst, cands, device: int = 0) -> np.ndarray:
     """d(trial_c, dst) for every candidate reversal (i, j) of one pair (grimm -t 1's inner loop)."""
     s = _i32(src)
@@ -181,6 +202,11 @@ def signed_inverse_dev(d_genomes: int, G: int, n: int, d_sinv: int, stream: int)
 def dist_pairs_dev(d_genomes: int, d_sinv: int, n: int, d_pairs: int, npairs: int, d_out: int,
                    stride: int, stream: int) -> None:
     _check(lib().grsr_dist_pairs_dev(d_genomes, d_sinv, n, d_pairs, npairs, d_out, stride, stream))
+
+
+def dist_pairs_sorted_dev(d_genomes: int, d_sinv: int, n: int, d_pairs: int, npairs: int, d_out: int,
+                          stride: int, stream: int) -> None:
+    _check(lib().grsr_dist_pairs_sorted_dev(d_genomes, d_sinv, n, d_pairs, npairs, d_out, stride, stream))
 
 
 def triangle_pairs_dev(G: int, first: int, count: int, d_pairs: int, stream: int) -> None:

@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -60,30 +61,16 @@ int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
-struct DevBuf {
-  void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  int alloc(size_t bytes) {
-    if (p) { cudaFree(p); p = nullptr; }
-    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
-    if (e != cudaSuccess) {
-      p = nullptr;
-      return fail(GRSR_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-    }
-    return GRSR_OK;
-  }
-};
-
 // Per-device working set of the host-buffer entry points: one stream and grow-only buffers that
 // survive between calls (a distance matrix call is ~20 ms of kernel time; allocating and freeing
 // 20 MB around it would cost as much again).  One call at a time per device (mutex).
-const int kCacheSlots = 8;   // 0 genomes, 1 inverses, 2 pairs, 3 results, 4-5 large-build scratch, 6 error word,
-                             // 7 deferred-pair list of the two-tier distance path
+const int kCacheSlots = 11;  // 0 genomes, 1 inverses, 2 pairs, 3 results, 4-5 large-build scratch, 6 error word,
+                             // 7 unused, 8 distance matrix, 9 stepwise state, 10 pair tickets
 struct DevCache {
   std::recursive_mutex mu;
   cudaStream_t stream = nullptr;
-  void *buf[kCacheSlots] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  size_t cap[kCacheSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void *buf[kCacheSlots] = {};
+  size_t cap[kCacheSlots] = {};
 };
 const int kMaxDevices = 64;
 DevCache g_cache[kMaxDevices];
@@ -103,6 +90,44 @@ int cache_reserve(DevCache &c, int slot, size_t bytes, void **out) {
 
 struct Launch { int threads; int ept; int grid; size_t smem; };
 
+// cudaFuncSetAttribute + cudaOccupancyMaxActiveBlocksPerMultiprocessor cost microseconds each and a
+// distance call asks dozens of times (every candidate block shape of the walk kernels): remembered
+// per (kernel, device, threads, dynamic shared memory).
+struct OccKey {
+  const void *fn; int dev, threads; size_t smem;
+  bool operator<(const OccKey &o) const {
+    if (fn != o.fn) return fn < o.fn;
+    if (dev != o.dev) return dev < o.dev;
+    if (threads != o.threads) return threads < o.threads;
+    return smem < o.smem;
+  }
+};
+std::mutex g_occ_mu;
+std::map<OccKey, int> g_occ;
+std::map<std::pair<const void *, int>, size_t> g_smem_set;   // largest dynamic smem opted in per (kernel, device)
+
+template <class K>
+int cached_occupancy(K kernel, int dev, int threads, size_t smem, int *occ) {
+  std::lock_guard<std::mutex> lk(g_occ_mu);
+  const void *fn = (const void *)kernel;
+  OccKey key = {fn, dev, threads, smem};
+  size_t &have = g_smem_set[std::make_pair(fn, dev)];
+  auto it = g_occ.find(key);
+  if (it != g_occ.end() && have >= smem) { *occ = it->second; return GRSR_OK; }
+  if (have == 0)
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            (int)cudaSharedmemCarveoutMaxShared));
+  if (have < smem || have == 0) {
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem ? smem : 1;
+  }
+  int o = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, threads, smem));
+  g_occ[key] = o;
+  *occ = o;
+  return GRSR_OK;
+}
+
 // Shape, shared memory and grid of a one-pair-per-block kernel instance `kernel` (already
 // specialised for L.ept): opt in to the large carve-out, ask the occupancy calculator how many
 // blocks stay resident per SM and launch a whole number of resident waves (148 SMs x occupancy).
@@ -116,11 +141,8 @@ int finish_plan(K kernel, long long units, Launch &L) {
   if (L.smem > (size_t)di.smem_optin)
     return fail(GRSR_ERR_TOOLARGE, "%zu bytes of shared memory per pair exceed the device limit %d",
                 L.smem, di.smem_optin);
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          (int)cudaSharedmemCarveoutMaxShared));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, L.threads, L.smem));
+  if ((rc = cached_occupancy(kernel, dev, L.threads, L.smem, &occ))) return rc;
   if (occ < 1) return fail(GRSR_ERR_CUDA, "kernel does not fit on an SM (smem %zu)", L.smem);
   int cap = env_int("GRSR_OCC", occ);
   if (cap >= 1 && cap < occ) occ = cap;
@@ -143,8 +165,6 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                          (int)cudaSharedmemCarveoutMaxShared));
   // The private-row kernel takes the shape with the most resident warps (few large blocks first: less
   // reserved shared memory).  In the shared-row kernel a block waits for its slowest warp at every run
   // of equal pi rows, so it takes the SMALLEST block that reaches 85 % of the best warp count
@@ -152,15 +172,15 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   int best_wpb = 0, best_occ = 0;
   const int forced = env_int(shared ? "GRSR_WALK_SHARED_WPB" : "GRSR_WALK_WPB", 0);
   int occ_of[33] = {0};
+  // opt in once to the largest shape so that the per-shape queries below never lower the attribute
   for (int k = 0; k < (shared ? 32 : 8); k++) {
     const int wpb = shared ? k + 1 : 8 - k;
     if (forced && wpb != forced) continue;
     const size_t smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * wpb
                                : grsr::walk_warp_bytes(n) * wpb;
     if (smem > (size_t)di.smem_optin) continue;
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, wpb * 32, smem));
+    if ((rc = cached_occupancy(kernel, dev, wpb * 32, smem, &occ))) return rc;
     occ_of[wpb] = occ;
     if (occ * wpb > best_occ * best_wpb) { best_wpb = wpb; best_occ = occ; }
   }
@@ -180,7 +200,6 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   P.smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * best_wpb
                   : grsr::walk_warp_bytes(n) * best_wpb;
   P.warps_per_sm = best_wpb * best_occ;
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   long long g = (long long)di.sms * best_occ, need = (npairs + best_wpb - 1) / best_wpb;
   if (g > need) g = need;
   if (g < 1) g = 1;
@@ -192,6 +211,14 @@ const int kMaxLargeGenes = 1000000;   // global-memory build: 31-bit ids, 21-bit
 
 // which build serves num_genes = n: the shared-memory one while the pair's graph fits on chip,
 // the global-memory one beyond (or when GRSR_FORCE_LARGE is set, for tests)
+size_t smem_budget() {
+  int dev = 0;
+  DevInfo di;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 227u * 1024u; }
+  if (dev_info(dev, di) != GRSR_OK || di.smem_optin <= 0) return 227u * 1024u;
+  return (size_t)di.smem_optin;
+}
+
 bool small_fits(int n, bool scenario) {
   if (env_int("GRSR_FORCE_LARGE", 0)) return false;
   if (n > grsr::kMaxSmemGenes || 2 * n + 2 > 32767) return false;
@@ -200,7 +227,7 @@ bool small_fits(int n, bool scenario) {
   if (t * e < 2 * n + 2) return false;
   size_t smem = scenario ? grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n)
                          : grsr::work_bytes(n, t * e, false) + grsr::stage_bytes(n);
-  return smem <= 227u * 1024u;
+  return smem <= smem_budget();
 }
 
 int check_genes_fit(int n) {
@@ -332,43 +359,49 @@ __global__ void validate_duplicates(const int32_t *__restrict__ genomes, const i
   }
 }
 
-__global__ void positions_to_signed_inverse(const int32_t *__restrict__ genomes, int32_t *slot,
-                                            long long total, int n) {
+// Pass 3.  If an offence was recorded the table must not reach the distance kernels (they index
+// shared memory with its genes): the DEVICE COPY is then overwritten with identity rows, so that the
+// launches already queued behind this one run on harmless data while the host learns of the error
+// from the word it reads back together with the results.
+__global__ void positions_to_signed_inverse(int32_t *__restrict__ genomes, int32_t *slot,
+                                            long long total, int n,
+                                            const unsigned long long *__restrict__ err) {
   long long stride = (long long)gridDim.x * blockDim.x;
+  const bool bad = (*err != ~0ull);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
     long long row = e / n;
+    if (bad) { int v = (int)(e - row * n) + 1; genomes[e] = v; slot[e] = v; continue; }
     int pos = slot[e];
     slot[e] = genomes[row * n + pos] > 0 ? (pos + 1) : -(pos + 1);
   }
 }
 
-// Validates the resident genome table and leaves its signed inverses in d_sinv.  One 8-byte
-// device-to-host read; on an offence the message uses the reference's wording.
-int validate_and_invert(const int32_t *genomes_host, const int32_t *d_genomes, int G, int n,
-                        int32_t *d_sinv, unsigned long long *d_err, cudaStream_t st) {
+// Validates the resident genome table and leaves its signed inverses in d_sinv.  Nothing here
+// waits for the device: *d_err (~0 = table is fine) is read back by the caller with its results and
+// turned into the reference's message by validation_error().
+int validate_and_invert(int32_t *d_genomes, int G, int n, int32_t *d_sinv, unsigned long long *d_err,
+                        cudaStream_t st) {
   long long total = (long long)G * n;
   int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  unsigned long long err = ~0ull;
   CK(cudaMemsetAsync(d_sinv, 0x7f, (size_t)total * sizeof(int32_t), st));
   CK(cudaMemsetAsync(d_err, 0xff, sizeof(unsigned long long), st));
   validate_first_positions<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n, d_err);
   validate_duplicates<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n, d_err);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(&err, d_err, sizeof err, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if (err != ~0ull) {
-    long long row = (long long)(err >> 34);
-    int pos = (int)((err >> 2) & 0xFFFFFFFFull), kind = (int)(err & 3ull);
-    long long g = genomes_host[row * n + pos], a = g < 0 ? -g : g;
-    if (kind == 0) return fail(GRSR_ERR_INVALID, "genome %lld: input gene == 0", row + 1);
-    if (kind == 1)
-      return fail(GRSR_ERR_INVALID, "genome %lld: input gene (%lld) larger than number of genes %d",
-                  row + 1, g, n);
-    return fail(GRSR_ERR_INVALID, "genome %lld: duplicate gene (%lld)", row + 1, a);
-  }
-  positions_to_signed_inverse<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n);
+  positions_to_signed_inverse<<<blocks, 256, 0, st>>>(d_genomes, d_sinv, total, n, d_err);
   CK(cudaGetLastError());
   return GRSR_OK;
+}
+
+int validation_error(unsigned long long err, const int32_t *genomes_host, int n) {
+  if (err == ~0ull) return GRSR_OK;
+  long long row = (long long)(err >> 34);
+  int pos = (int)((err >> 2) & 0xFFFFFFFFull), kind = (int)(err & 3ull);
+  long long g = genomes_host[row * n + pos], a = g < 0 ? -g : g;
+  if (kind == 0) return fail(GRSR_ERR_INVALID, "genome %lld: input gene == 0", row + 1);
+  if (kind == 1)
+    return fail(GRSR_ERR_INVALID, "genome %lld: input gene (%lld) larger than number of genes %d",
+                row + 1, g, n);
+  return fail(GRSR_ERR_INVALID, "genome %lld: duplicate gene (%lld)", row + 1, a);
 }
 
 // check_genes of the reference (G/mcread_input.c:83-135): every row a signed permutation of 1..n
@@ -397,13 +430,59 @@ int check_genomes(const int32_t *genomes, long long rows, int n) {
   return GRSR_OK;
 }
 
+// The device's default memory pool keeps what is freed (release threshold = everything), so that the
+// per-call cudaMallocAsync / cudaFreeAsync of the distance path costs no driver allocation after the
+// first call.
+int pool_ready(int dev) {
+  static std::mutex mu;
+  static bool done[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0 || dev >= kMaxDevices || done[dev]) return GRSR_OK;
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  unsigned long long keep = ~0ull;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  done[dev] = true;
+  return GRSR_OK;
+}
+
 enum PairSource { PAIRS_LIST, PAIRS_TRIANGLE, PAIRS_SQUARE };
 
-// One device's share of a pair job: copy the genome table in, build the signed inverses, obtain the
-// pair slice (copied or generated on the device), run the kernel, copy the results out.
+int dist_pairs_dev_impl(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
+                        const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
+                        cudaStream_t st, int order_hint);
+
+// The caller's current device is left as it was found (the host-buffer entry points switch devices).
+struct DeviceGuard {
+  int saved = -1;
+  DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+  ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
+// Lets kernels on device `dev` store into / draw tickets from memory of device `owner` (NVLink peer
+// mapping).  False when the two devices cannot do that.
+bool peer_ok(int dev, int owner) {
+  if (dev == owner) return true;
+  int can = 0;
+  if (cudaDeviceCanAccessPeer(&can, dev, owner) != cudaSuccess || !can) { cudaGetLastError(); return false; }
+  int cur = -1;
+  cudaGetDevice(&cur);
+  if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+  if (cur >= 0) cudaSetDevice(cur);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return true; }
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
+// One device's share of a pair job: copy the genome table in, validate it and build the signed
+// inverses, obtain the pair slice (copied or generated on the device), run the kernels, copy the
+// results out -- one stream, one synchronisation at the end; the validation verdict travels back
+// with the results.  stride 1 / 5: results go to out_host.  stride -G (matrix mode): the kernels
+// scatter d into d_matrix[i][j] and [j][i] themselves; d_matrix may belong to another device.
 int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSource src,
                         const int32_t *pairs_host, long long first, long long count,
-                        int32_t *out_host, int stride) {
+                        int32_t *out_host, int stride, int32_t *d_matrix) {
   if (count <= 0) return GRSR_OK;
   if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
@@ -412,18 +491,14 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
   if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   cudaStream_t st = c.stream;
   size_t gbytes = (size_t)G * n * sizeof(int32_t);
-  void *dg, *ds, *dp, *dout;
+  void *dg, *ds, *dp, *dout = nullptr, *derr;
   int rc;
   if ((rc = cache_reserve(c, 0, gbytes, &dg)) || (rc = cache_reserve(c, 1, gbytes, &ds)) ||
       (rc = cache_reserve(c, 2, (size_t)count * 2 * sizeof(int32_t), &dp)) ||
-      (rc = cache_reserve(c, 3, (size_t)count * stride * sizeof(int32_t), &dout)))
+      (rc = cache_reserve(c, 6, sizeof(unsigned long long), &derr)))
     return rc;
-  void *derr;
-  if ((rc = cache_reserve(c, 6, sizeof(unsigned long long), &derr))) return rc;
-  CK(cudaMemcpyAsync(dg, genomes, gbytes, cudaMemcpyHostToDevice, st));
-  if ((rc = validate_and_invert(genomes, (const int32_t *)dg, G, n, (int32_t *)ds,
-                                (unsigned long long *)derr, st)))
-    return rc;
+  if (stride > 0 && (rc = cache_reserve(c, 3, (size_t)count * stride * sizeof(int32_t), &dout))) return rc;
+  // the pair slice does not depend on the table: it is generated while the table is still in flight
   if (src == PAIRS_LIST) {
     CK(cudaMemcpyAsync(dp, pairs_host + 2 * first, (size_t)count * 2 * sizeof(int32_t),
                        cudaMemcpyHostToDevice, st));
@@ -434,51 +509,190 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
     square_pairs_kernel<<<blocks, 256, 0, st>>>(G, first, count, (int32_t *)dp);
     CK(cudaGetLastError());
   }
-  if ((rc = grsr_dist_pairs_dev((const int32_t *)dg, (const int32_t *)ds, n, (const int32_t *)dp,
-                                count, (int32_t *)dout, stride, st)))
+  CK(cudaMemcpyAsync(dg, genomes, gbytes, cudaMemcpyHostToDevice, st));
+  if ((rc = validate_and_invert((int32_t *)dg, G, n, (int32_t *)ds, (unsigned long long *)derr, st)))
     return rc;
-  CK(cudaMemcpyAsync(out_host, dout, (size_t)count * stride * sizeof(int32_t),
-                     cudaMemcpyDeviceToHost, st));
+  // the triangle is sorted by pi row by construction: no order test on the device
+  const int hint = (src == PAIRS_TRIANGLE) ? 1 : (src == PAIRS_SQUARE ? 0 : -1);
+  if ((rc = dist_pairs_dev_impl((const int32_t *)dg, (const int32_t *)ds, n, (const int32_t *)dp, count,
+                                stride > 0 ? (int32_t *)dout : d_matrix, stride, st, hint)))
+    return rc;
+  unsigned long long err = ~0ull;
+  if (stride > 0)
+    CK(cudaMemcpyAsync(out_host, dout, (size_t)count * stride * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&err, derr, sizeof err, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return validation_error(err, genomes, n);
+}
+
+// Runs work(d) for d = 0 .. ngpus-1, device first_device + d: d = 0 on the calling thread, the others
+// on one host thread each; the first error (lowest device) is reported.
+template <class F>
+int on_devices(int first_device, int ngpus, F work) {
+  std::vector<int> rcs(ngpus, 0);
+  std::vector<std::string> errs(ngpus);
+  std::vector<std::thread> th;
+  for (int d = 1; d < ngpus; d++)
+    th.emplace_back([&, d]() { rcs[d] = work(d); if (rcs[d]) errs[d] = g_err; });
+  rcs[0] = work(0);
+  if (rcs[0]) errs[0] = g_err;
+  for (auto &t : th) t.join();
+  for (int d = 0; d < ngpus; d++) {
+    if (!rcs[d]) continue;
+    if (ngpus == 1) return fail(rcs[d], "%s", errs[d].c_str());
+    return fail(rcs[d], "device %d: %s", first_device + d, errs[d].c_str());
+  }
   return GRSR_OK;
 }
 
 // Split [0, total) into ngpus contiguous slices, one host thread per device; no data-path collective.
 int shard_pairs(const int32_t *genomes, int G, int n, PairSource src, const int32_t *pairs_host,
                 long long total, int32_t *out_host, int stride, int first_device, int ngpus) {
-  if (ngpus == 1)
-    return run_pairs_on_device(first_device, genomes, G, n, src, pairs_host, 0, total, out_host,
-                               stride);
-  std::vector<int> rcs(ngpus, 0);
-  std::vector<std::string> errs(ngpus);
-  std::vector<std::thread> th;
-  for (int d = 0; d < ngpus; d++) {
+  return on_devices(first_device, ngpus, [&](int d) {
     long long lo = total * d / ngpus, hi = total * (d + 1) / ngpus;
-    th.emplace_back([&, d, lo, hi]() {
-      rcs[d] = run_pairs_on_device(first_device + d, genomes, G, n, src, pairs_host, lo, hi - lo,
-                                   out_host + lo * stride, stride);
-      if (rcs[d]) errs[d] = g_err;
-    });
+    return run_pairs_on_device(first_device + d, genomes, G, n, src, pairs_host, lo, hi - lo,
+                               out_host + lo * stride, stride, nullptr);
+  });
+}
+
+// setinvmatrix on ngpus devices.  The G x G matrix lives on the first device; every device's kernels
+// store their distances straight into it, both [i][j] and [j][i] (the other devices through NVLink
+// peer mappings, 8 bytes per pair), the first device zeroes the diagonal, and ONE device-to-host copy
+// delivers the matrix.  Without peer access between the devices: flat slices to the host and a host
+// scatter.
+int matrix_on_devices(const int32_t *genomes, int G, int n, int32_t *distmatrix, int first_device,
+                      int ngpus) {
+  const long long P = (long long)G * (G - 1) / 2;
+  bool peers = true;
+  for (int d = 1; d < ngpus; d++) peers = peers && peer_ok(first_device + d, first_device);
+  if (env_int("GRSR_NO_PEER", 0)) peers = (ngpus == 1);
+  if (!peers) {
+    std::vector<int32_t> flat((size_t)P);
+    int rc = shard_pairs(genomes, G, n, PAIRS_TRIANGLE, nullptr, P, flat.data(), 1, first_device, ngpus);
+    if (rc) return rc;
+    long long p = 0;
+    for (long long j = 0; j < G; j++) {
+      distmatrix[j * G + j] = 0;
+      for (long long i = 0; i < j; i++, p++) distmatrix[i * G + j] = distmatrix[j * G + i] = flat[p];
+    }
+    return GRSR_OK;
   }
-  for (auto &t : th) t.join();
-  for (int d = 0; d < ngpus; d++)
-    if (rcs[d]) return fail(rcs[d], "device %d: %s", first_device + d, errs[d].c_str());
+  CK(cudaSetDevice(first_device));
+  DevCache &c = g_cache[first_device];
+  std::lock_guard<std::recursive_mutex> lk(c.mu);       // held for the whole call: the matrix is ours
+  if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  void *dmat;
+  int rc = cache_reserve(c, 8, (size_t)G * G * sizeof(int32_t), &dmat);
+  if (rc) return rc;
+  CK(cudaMemset2DAsync(dmat, (size_t)(G + 1) * sizeof(int32_t), 0, sizeof(int32_t), (size_t)G, c.stream));
+  rc = on_devices(first_device, ngpus, [&](int d) {
+    long long lo = P * d / ngpus, hi = P * (d + 1) / ngpus;
+    return run_pairs_on_device(first_device + d, genomes, G, n, PAIRS_TRIANGLE, nullptr, lo, hi - lo,
+                               nullptr, -G, (int32_t *)dmat);
+  });
+  if (rc) return rc;
+  CK(cudaSetDevice(first_device));
+  CK(cudaMemcpyAsync(distmatrix, dmat, (size_t)G * G * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
   return GRSR_OK;
 }
 
-// One device's share of a scenario batch: copy the pairs in, run the persistent scenario kernel,
-// copy the step lists out.
+// ---- scenarios ----------------------------------------------------------------------------------------
+
+// Results of a scenario call are written by the kernels straight into page-locked host memory that
+// every device maps (8 bytes per emitted step: nothing next to a step's cost), so that any device
+// can serve any pair of the call's queue.  One grow-only arena per process; a scenario call owns it
+// from start to end (scenario calls are serialised process-wide).
+struct HostArena {
+  std::mutex mu;
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes, void **out) {
+    if (cap < bytes) {
+      if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+      size_t want = bytes + bytes / 4 + 4096;
+      cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable | cudaHostAllocMapped);
+      if (e != cudaSuccess) {
+        p = nullptr;
+        return fail(GRSR_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+      }
+      cap = want;
+    }
+    *out = p;
+    return GRSR_OK;
+  }
+};
+HostArena g_arena;
+
+struct ScenOut {                 // views into the arena
+  int32_t *steps;                // npairs x max_steps x 2
+  int32_t *nsteps, *status;      // npairs
+  unsigned long long *evals;     // npairs
+};
+
+// Few pairs, on-chip sizes: while a pair's graph has hurdles (every breakpoint pair must be
+// evaluated, hundreds to thousands per step) each step's evaluations are spread over the whole GPU
+// (grsr_stepwise.cuh); the hurdle-free rest of every pair is left to the persistent kernel.
+// d_src is the device copy of the sources (advanced in place).
+int stepwise_prefix(DevCache &c, cudaStream_t st, int32_t *d_src, const int32_t *d_dst, int npairs, int n,
+                    const ScenOut &O, int max_steps, const Launch &L) {
+  const int cap = (2 * (n + 1) > 4096) ? 2 * (n + 1) : 4096;
+  void *dstate, *dcands, *dd2;
+  int r;
+  if ((r = cache_reserve(c, 9, sizeof(grsr::StepState), &dstate)) ||
+      (r = cache_reserve(c, 2, (size_t)cap * 2 * sizeof(int32_t), &dcands)) ||
+      (r = cache_reserve(c, 3, (size_t)cap * sizeof(int32_t), &dd2)))
+    return r;
+  Launch LT;
+  LT.threads = L.threads; LT.ept = L.ept;
+  LT.smem = grsr::work_bytes(n, L.threads * L.ept, false) + 2 * grsr::scen_arr_bytes(n);
+  GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::trial_batch_kernel<kNt, kEpt>, cap, LT));
+  if (r) return r;
+  { Launch LPp = L;
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::step_prepare_kernel<kNt, kEpt>, 1, LPp));
+    if (r) return r; }
+  const int32_t *ncand_dev = (const int32_t *)((const char *)dstate + offsetof(grsr::StepState, ncand));
+  for (int p = 0; p < npairs; p++) {
+    grsr::StepState hs;
+    memset(&hs, 0, sizeof hs);
+    hs.lastkey = ~0ull; hs.batch_end = ~0ull;
+    CK(cudaMemcpyAsync(dstate, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
+    int32_t *cur_p = d_src + (size_t)p * n;
+    const int32_t *dst_p = d_dst + (size_t)p * n;
+    int32_t *steps_p = O.steps + 2 * (size_t)p * max_steps;
+    for (;;) {
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::step_prepare_kernel<kNt, kEpt><<<1, L.threads, L.smem, st>>>(
+          cur_p, dst_p, n, (grsr::StepState *)dstate, (int32_t *)dcands, cap)));
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<LT.grid, LT.threads, LT.smem, st>>>(
+          cur_p, dst_p, n, (const int32_t *)dcands, 0LL, (int32_t *)dd2, ncand_dev)));
+      grsr::step_select_kernel<<<1, 256, 0, st>>>(cur_p, n, (grsr::StepState *)dstate,
+                                                  (const int32_t *)dcands, (const int32_t *)dd2,
+                                                  steps_p, max_steps);
+      CK(cudaGetLastError());
+      CK(cudaMemcpyAsync(&hs, dstate, sizeof hs, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (hs.d == 0 || hs.status != GRSR_SCEN_OK || hs.h == 0) break;
+    }
+    O.nsteps[p] = hs.nsteps;
+    O.evals[p] = hs.evals;
+    O.status[p] = hs.status;      // OVERFLOW / STUCK end the pair here; the persistent kernel skips it
+  }
+  return GRSR_OK;
+}
+
+// One device's part of a scenario call: copy all pairs in, run the persistent kernel on the queue.
 int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npairs, int n,
-                       grsr_step_t *steps, int32_t *nsteps, int max_steps) {
-  if (npairs <= 0) return GRSR_OK;
+                       const ScenOut &O, int max_steps, grsr::PairQueue queue, bool stepwise) {
   if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
-  // one scenario call at a time per device: the global-memory build's workspace is shared
-  std::lock_guard<std::recursive_mutex> device_lock(g_cache[dev].mu);
+  DevCache &c = g_cache[dev];
+  std::lock_guard<std::recursive_mutex> device_lock(c.mu);   // the global-memory build's workspace is per device
+  if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t st = c.stream;
   DevInfo di;
   int rc = dev_info(dev, di);
   if (rc) return rc;
-  if ((rc = check_genes_fit(n))) return rc;
   const bool small = small_fits(n, true);
   Launch L;
   L.threads = 1024; L.ept = 0; L.smem = 0; L.grid = 1;
@@ -498,109 +712,196 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
                     grsr::scen_large_bytes(n), dev, LP);
   }
   if (rc) return rc;
-  cudaStream_t st;
-  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  DevBuf dsrc, ddst, dsteps, dns, dstat, dtick;
+  void *dsrc, *ddst;
   size_t gbytes = (size_t)npairs * n * sizeof(int32_t);
-  size_t sbytes = (size_t)npairs * (max_steps > 0 ? max_steps : 1) * sizeof(grsr_step_t);
-  if ((rc = dsrc.alloc(gbytes)) || (rc = ddst.alloc(gbytes)) || (rc = dsteps.alloc(sbytes)) ||
-      (rc = dns.alloc((size_t)npairs * 4)) || (rc = dstat.alloc((size_t)npairs * 4)) ||
-      (rc = dtick.alloc(4))) {
-    cudaStreamDestroy(st);
-    return rc;
+  if ((rc = cache_reserve(c, 0, gbytes, &dsrc)) || (rc = cache_reserve(c, 1, gbytes, &ddst))) return rc;
+  CK(cudaMemcpyAsync(dsrc, src, gbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ddst, dst, gbytes, cudaMemcpyHostToDevice, st));
+  int resume = 0;
+  if (stepwise && small) {
+    if ((rc = stepwise_prefix(c, st, (int32_t *)dsrc, (const int32_t *)ddst, npairs, n, O, max_steps, L)))
+      return rc;
+    resume = 1;
   }
-  std::vector<int32_t> stat((size_t)npairs);
-  auto body = [&]() -> int {
-    CK(cudaMemcpyAsync(dsrc.p, src, gbytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ddst.p, dst, gbytes, cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(dtick.p, 0, 4, st));
-    int resume = 0;
-    if (small && npairs <= env_int("GRSR_STEPWISE_MAX", 16)) {
-      // Few pairs: while a pair's graph has hurdles (every breakpoint pair must be evaluated, hundreds
-      // to thousands per step) spread each step's evaluations over the whole GPU; hand the
-      // hurdle-free rest of every pair to the persistent kernel below (grsr_stepwise.cuh).
-      const int cap = (2 * (n + 1) > 4096) ? 2 * (n + 1) : 4096;
-      DevBuf dstate, dcands, dd2;
-      int r;
-      if ((r = dstate.alloc(sizeof(grsr::StepState))) || (r = dcands.alloc((size_t)cap * 2 * sizeof(int32_t))) ||
-          (r = dd2.alloc((size_t)cap * sizeof(int32_t))))
-        return r;
-      Launch LT;
-      LT.threads = L.threads; LT.ept = L.ept;
-      LT.smem = grsr::work_bytes(n, L.threads * L.ept, false) + 2 * grsr::scen_arr_bytes(n);
-      GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::trial_batch_kernel<kNt, kEpt>, cap, LT));
-      if (r) return r;
-      { Launch LPp = L;
-        GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::step_prepare_kernel<kNt, kEpt>, 1, LPp));
-        if (r) return r; }
-      std::vector<int32_t> ns0((size_t)npairs, 0);
-      const int32_t *ncand_dev = (const int32_t *)((const char *)dstate.p + offsetof(grsr::StepState, ncand));
-      for (int p = 0; p < npairs; p++) {
-        grsr::StepState hs;
-        memset(&hs, 0, sizeof hs);
-        hs.lastkey = ~0ull; hs.batch_end = ~0ull;
-        CK(cudaMemcpyAsync(dstate.p, &hs, sizeof hs, cudaMemcpyHostToDevice, st));
-        int32_t *cur_p = (int32_t *)dsrc.p + (size_t)p * n;
-        const int32_t *dst_p = (const int32_t *)ddst.p + (size_t)p * n;
-        int32_t *steps_p = (int32_t *)dsteps.p + 2 * (size_t)p * max_steps;
-        for (;;) {
-          GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::step_prepare_kernel<kNt, kEpt><<<1, L.threads, L.smem, st>>>(
-              cur_p, dst_p, n, (grsr::StepState *)dstate.p, (int32_t *)dcands.p, cap)));
-          GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<LT.grid, LT.threads, LT.smem, st>>>(
-              cur_p, dst_p, n, (const int32_t *)dcands.p, 0LL, (int32_t *)dd2.p, ncand_dev)));
-          grsr::step_select_kernel<<<1, 256, 0, st>>>(cur_p, n, (grsr::StepState *)dstate.p,
-                                                      (const int32_t *)dcands.p, (const int32_t *)dd2.p,
-                                                      steps_p, max_steps);
-          CK(cudaGetLastError());
-          CK(cudaMemcpyAsync(&hs, dstate.p, sizeof hs, cudaMemcpyDeviceToHost, st));
-          CK(cudaStreamSynchronize(st));
-          if (hs.d == 0 || hs.status != GRSR_SCEN_OK || hs.h == 0) break;
-        }
-        ns0[p] = hs.nsteps;
-        if (hs.status == GRSR_SCEN_OVERFLOW)
-          return fail(GRSR_ERR_INVALID, "pair %d: scenario needs more than max_steps=%d steps", p, max_steps);
-        if (hs.status == GRSR_SCEN_STUCK)
-          return fail(GRSR_ERR_SEARCH, "pair %d: reversals ended prematurely after %d steps", p, hs.nsteps);
-      }
-      CK(cudaMemcpyAsync(dns.p, ns0.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice, st));
-      CK(cudaStreamSynchronize(st));      // ns0 leaves scope
-      resume = 1;
+  if (small) {
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
+        (const int32_t *)dsrc, (const int32_t *)ddst, npairs, n, O.steps, O.nsteps, max_steps, O.status,
+        O.evals, queue, resume)));
+  } else if (LP.cs == 1) {
+    grsr::scenario_large_kernel<<<LP.grid, 1024, 0, st>>>(
+        (const int32_t *)dsrc, (const int32_t *)ddst, npairs, n, O.steps, O.nsteps, max_steps, O.status,
+        O.evals, queue, (unsigned char *)LP.scratch);
+  } else {
+    int r = launch_cluster(grsr::scenario_cluster_kernel, LP, st, (const int32_t *)dsrc,
+                           (const int32_t *)ddst, npairs, n, O.steps, O.nsteps, max_steps, O.status,
+                           O.evals, queue, (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
+    if (r) return r;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  return GRSR_OK;
+}
+
+// The scenario call behind grsr_scenario_batch / grsr_scenario_prefix.  All devices draw pairs from
+// ONE ticket (a word in the first device's memory, reached by the others through NVLink peer mapping
+// with system-scope atomics): per-pair work differs by orders of magnitude, so any static split would
+// leave devices idle.  Without peer access: interleaved split (pair p on device p mod ngpus).
+int scenario_call(const int32_t *src, const int32_t *dst, int npairs, int n, grsr_step_t *steps,
+                  int32_t *nsteps, int max_steps, int32_t *complete, int64_t *evals, bool prefix,
+                  int first_device, int ngpus) {
+  int rc = check_genes_fit(n);
+  if (rc) return rc;
+  std::lock_guard<std::mutex> arena_lock(g_arena.mu);
+  const size_t ms = (size_t)(max_steps > 0 ? max_steps : 1);
+  const size_t sbytes = (((size_t)npairs * ms * 2 * sizeof(int32_t)) + 15) & ~(size_t)15;
+  const size_t ibytes = (((size_t)npairs * sizeof(int32_t)) + 15) & ~(size_t)15;
+  void *base;
+  if ((rc = g_arena.reserve(sbytes + 2 * ibytes + (size_t)npairs * sizeof(unsigned long long), &base))) return rc;
+  ScenOut O;
+  O.steps = (int32_t *)base;
+  O.nsteps = (int32_t *)((char *)base + sbytes);
+  O.status = (int32_t *)((char *)base + sbytes + ibytes);
+  O.evals = (unsigned long long *)((char *)base + sbytes + 2 * ibytes);
+  memset(O.nsteps, 0, 2 * ibytes + (size_t)npairs * sizeof(unsigned long long));
+
+  CK(cudaSetDevice(first_device));
+  const bool stepwise = npairs <= env_int("GRSR_STEPWISE_MAX", 16);
+  if (stepwise) ngpus = 1;                              // a handful of pairs: one device, whole-GPU steps
+  bool peers = true;
+  for (int d = 1; d < ngpus; d++) peers = peers && peer_ok(first_device + d, first_device);
+  if (env_int("GRSR_NO_PEER", 0)) peers = (ngpus == 1);
+  // tickets: word d of a small buffer on the first device (word 0 is the shared queue)
+  DevCache &c0 = g_cache[first_device];
+  void *dtick;
+  {
+    std::lock_guard<std::recursive_mutex> lk(c0.mu);
+    if (!c0.stream) CK(cudaStreamCreateWithFlags(&c0.stream, cudaStreamNonBlocking));
+    if ((rc = cache_reserve(c0, 10, 256, &dtick))) return rc;
+    CK(cudaMemsetAsync(dtick, 0, 256, c0.stream));
+    CK(cudaStreamSynchronize(c0.stream));               // zero before any device draws
+  }
+  rc = on_devices(first_device, ngpus, [&](int d) -> int {
+    grsr::PairQueue q;
+    if (peers) { q.ticket = (unsigned int *)dtick; q.first = 0; q.stride = 1; }
+    else {
+      // private queue per device (its own ticket word is allocated on that device)
+      int dev = first_device + d, r;
+      void *own;
+      CK(cudaSetDevice(dev));
+      { std::lock_guard<std::recursive_mutex> lk(g_cache[dev].mu);
+        if (!g_cache[dev].stream) CK(cudaStreamCreateWithFlags(&g_cache[dev].stream, cudaStreamNonBlocking));
+        if ((r = cache_reserve(g_cache[dev], 10, 256, &own))) return r;
+        CK(cudaMemsetAsync(own, 0, 256, g_cache[dev].stream)); }
+      q.ticket = (unsigned int *)own; q.first = d; q.stride = ngpus;
     }
-    if (small) {
-      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::scenario_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
-          (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
-          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p, resume)));
-    } else if (LP.cs == 1) {
-      grsr::scenario_large_kernel<<<LP.grid, 1024, 0, st>>>(
-          (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n, (int32_t *)dsteps.p,
-          (int32_t *)dns.p, max_steps, (int32_t *)dstat.p, nullptr, (unsigned int *)dtick.p,
-          (unsigned char *)LP.scratch);
-    } else {
-      int r = launch_cluster(grsr::scenario_cluster_kernel, LP, st,
-                             (const int32_t *)dsrc.p, (const int32_t *)ddst.p, npairs, n,
-                             (int32_t *)dsteps.p, (int32_t *)dns.p, max_steps, (int32_t *)dstat.p,
-                             (unsigned long long *)nullptr, (unsigned int *)dtick.p,
-                             (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
-      if (r) return r;
-    }
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(steps, dsteps.p, sbytes, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(nsteps, dns.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(stat.data(), dstat.p, (size_t)npairs * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    return GRSR_OK;
-  };
-  rc = body();
-  cudaStreamDestroy(st);
+    return scenario_on_device(first_device + d, src, dst, npairs, n, O, max_steps, q, stepwise);
+  });
   if (rc) return rc;
   for (int p = 0; p < npairs; p++) {
-    if (stat[p] == GRSR_SCEN_OVERFLOW)
-      return fail(GRSR_ERR_INVALID, "pair %d: scenario needs more than max_steps=%d steps", p,
-                  max_steps);
-    if (stat[p] == GRSR_SCEN_STUCK)
-      return fail(GRSR_ERR_SEARCH, "pair %d: reversals ended prematurely after %d steps", p,
-                  nsteps[p]);
+    if (O.status[p] == GRSR_SCEN_STUCK)
+      return fail(GRSR_ERR_SEARCH, "pair %d: reversals ended prematurely after %d steps", p, O.nsteps[p]);
+    if (O.status[p] == GRSR_SCEN_OVERFLOW && !prefix)
+      return fail(GRSR_ERR_INVALID, "pair %d: scenario needs more than max_steps=%d steps", p, max_steps);
   }
+  for (int p = 0; p < npairs; p++) {
+    nsteps[p] = O.nsteps[p];
+    if (O.nsteps[p] > 0)
+      memcpy(steps + (size_t)p * max_steps, O.steps + 2 * (size_t)p * ms, (size_t)O.nsteps[p] * sizeof(grsr_step_t));
+    if (complete) complete[p] = (O.status[p] == GRSR_SCEN_OK) ? 1 : 0;
+    if (evals) evals[p] = (int64_t)O.evals[p];
+  }
+  return GRSR_OK;
+}
+
+// The batched distance on resident data.  stride 1 / 5 / -G as in put_result (grsr_core.cuh).
+// order_hint: 1 = the list is sorted by pi row (shared-row walk kernel), 0 = it is not (private rows),
+// -1 = unknown: walk_order_kernel counts the row changes and both kernels are launched, the one the
+// verdict does not name returns at once.
+int dist_pairs_dev_impl(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
+                        const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
+                        cudaStream_t st, int order_hint) {
+  if (npairs <= 0) return GRSR_OK;
+  if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
+  int rc = check_genes_fit(num_genes);
+  if (rc) return rc;
+  int dev0;
+  CK(cudaGetDevice(&dev0));
+  DevInfo di0;
+  if ((rc = dev_info(dev0, di0))) return rc;
+  // Two tiers when there are enough pairs to fill the chip with one warp per pair: the walk kernel
+  // settles every pair without hurdle candidates, the block-per-pair kernel takes the deferred rest.
+  const int walk_mode = env_int("GRSR_WALK", -1);
+  if (small_fits(num_genes, false) && walk_mode != 0 && (walk_mode == 1 || npairs >= di0.sms) &&
+      dev0 < kMaxDevices && npairs < (1ll << 31)) {
+    int order_mode = env_int("GRSR_WALK_SHARED", -1);
+    if (order_mode < 0) order_mode = order_hint;
+    WalkPlan WP, WS;
+    if (order_mode != 1 && (rc = plan_walk(grsr::dist_walk_kernel, false, num_genes, npairs, WP))) return rc;
+    if (order_mode != 0 && (rc = plan_walk(grsr::dist_walk_shared_kernel, true, num_genes, npairs, WS))) return rc;
+    Launch L;
+    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_deferred_kernel<kNt, kEpt>, npairs, L));
+    if (rc) return rc;
+    // Per-call scratch (deferred count, order verdict, tickets, deferred list) from the device's
+    // stream-ordered pool: calls in flight on different streams of one device never share it.
+    if ((rc = pool_ready(dev0))) return rc;
+    void *dq;
+    {
+      cudaError_t e = cudaMallocAsync(&dq, 256 + (size_t)npairs * sizeof(int32_t), st);
+      if (e != cudaSuccess)
+        return fail(GRSR_ERR_NOMEM, "cudaMallocAsync(%zu) failed: %s", 256 + (size_t)npairs * sizeof(int32_t),
+                    cudaGetErrorString(e));
+    }
+    unsigned *dcount = (unsigned *)dq;
+    unsigned *dflag = (order_mode < 0) ? (unsigned *)((char *)dq + 64) : nullptr;
+    unsigned *dtick_s = (unsigned *)((char *)dq + 128), *dtick_p = (unsigned *)((char *)dq + 192);
+    int32_t *dlist = (int32_t *)((char *)dq + 256);
+    CK(cudaMemsetAsync(dq, 0, 256, st));               // deferred count, pi-row change count, tickets
+    if (dflag) {
+      long long ob = (npairs + 255) / 256;
+      grsr::walk_order_kernel<<<(int)(ob < 592 ? ob : 592), 256, 0, st>>>(d_pairs, (long long)npairs, dflag);
+    }
+    if (order_mode != 0)
+      grsr::dist_walk_shared_kernel<<<WS.grid, WS.wpb * 32, WS.smem, st>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WS.shift, dlist, dcount, dflag, dtick_s);
+    if (order_mode != 1)
+      grsr::dist_walk_kernel<<<WP.grid, WP.wpb * 32, WP.smem, st>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WP.shift, dlist, dcount, dflag, dtick_p);
+    CK(cudaGetLastError());
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_deferred_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, dlist, dcount, d_out, stride)));
+    CK(cudaGetLastError());
+    CK(cudaFreeAsync(dq, st));
+  } else if (small_fits(num_genes, false)) {
+    Launch L;
+    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept, 8);
+    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
+    if (!rc && L.grid < npairs) {            // more pairs than resident blocks: throughput shape
+      grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+      L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
+    }
+    if (rc) return rc;
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, st>>>(
+        d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
+  } else {
+    LargePlan LP;
+    rc = plan_large(grsr::dist_pairs_large_kernel, grsr::dist_pairs_cluster_kernel, npairs,
+                    grsr::large_work_bytes(num_genes, false), dev0, LP);
+    if (rc) return rc;
+    if (LP.cs == 1) {
+      grsr::dist_pairs_large_kernel<<<LP.grid, 1024, 0, st>>>(
+          d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride, (unsigned char *)LP.scratch);
+    } else {
+      rc = launch_cluster(grsr::dist_pairs_cluster_kernel, LP, st, d_genomes, d_sinv,
+                          num_genes, d_pairs, (long long)npairs, d_out, stride,
+                          (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
+      if (rc) return rc;
+    }
+  }
+  CK(cudaGetLastError());
   return GRSR_OK;
 }
 
@@ -619,6 +920,11 @@ int grsr_device_count(void) {
 }
 
 void grsr_release(void) {
+  {
+    std::lock_guard<std::mutex> lk(g_arena.mu);
+    if (g_arena.p) { cudaFreeHost(g_arena.p); g_arena.p = nullptr; g_arena.cap = 0; }
+  }
+  DeviceGuard guard;
   for (int d = 0; d < kMaxDevices; d++) {
     DevCache &c = g_cache[d];
     std::lock_guard<std::recursive_mutex> lk(c.mu);
@@ -662,86 +968,17 @@ int grsr_triangle_pairs_dev(int num_genomes, int64_t first, int64_t count, int32
 int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
                         const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
                         void *stream) {
-  if (npairs <= 0) return GRSR_OK;
   if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
-  if (num_genes < 1) return fail(GRSR_ERR_INVALID, "num_genes must be positive");
-  int rc = check_genes_fit(num_genes);
-  if (rc) return rc;
-  int dev0;
-  CK(cudaGetDevice(&dev0));
-  DevInfo di0;
-  if ((rc = dev_info(dev0, di0))) return rc;
-  // Two tiers when there are enough pairs to fill the chip with one warp per pair: the walk kernel
-  // settles every pair without hurdle candidates, the block-per-pair kernel takes the deferred rest.
-  const int walk_mode = env_int("GRSR_WALK", -1);
-  if (small_fits(num_genes, false) && walk_mode != 0 && (walk_mode == 1 || npairs >= di0.sms) &&
-      dev0 < kMaxDevices && npairs < (1ll << 31)) {
-    // order_mode: -1 = decide on the device (walk_order_kernel), 0 = private rows, 1 = shared rows
-    const int order_mode = env_int("GRSR_WALK_SHARED", -1);
-    WalkPlan WP, WS;
-    if (order_mode != 1 && (rc = plan_walk(grsr::dist_walk_kernel, false, num_genes, npairs, WP))) return rc;
-    if (order_mode != 0 && (rc = plan_walk(grsr::dist_walk_shared_kernel, true, num_genes, npairs, WS))) return rc;
-    Launch L;
-    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
-    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
-    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_deferred_kernel<kNt, kEpt>, npairs, L));
-    if (rc) return rc;
-    void *dq;
-    {
-      DevCache &c = g_cache[dev0];
-      std::lock_guard<std::recursive_mutex> lk(c.mu);
-      if ((rc = cache_reserve(c, 7, 256 + (size_t)npairs * sizeof(int32_t), &dq))) return rc;
-    }
-    unsigned *dcount = (unsigned *)dq;
-    unsigned *dflag = (order_mode < 0) ? (unsigned *)((char *)dq + 64) : nullptr;
-    int32_t *dlist = (int32_t *)((char *)dq + 256);
-    cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(dq, 0, 128, st));               // deferred count and pi-row change count
-    if (dflag) {
-      long long ob = (npairs + 255) / 256;
-      grsr::walk_order_kernel<<<(int)(ob < 592 ? ob : 592), 256, 0, st>>>(d_pairs, (long long)npairs, dflag);
-    }
-    if (order_mode != 0)
-      grsr::dist_walk_shared_kernel<<<WS.grid, WS.wpb * 32, WS.smem, st>>>(
-          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WS.shift, dlist, dcount, dflag);
-    if (order_mode != 1)
-      grsr::dist_walk_kernel<<<WP.grid, WP.wpb * 32, WP.smem, st>>>(
-          d_genomes, d_sinv, num_genes, d_pairs, (long long)npairs, d_out, stride, WP.shift, dlist, dcount, dflag);
-    CK(cudaGetLastError());
-    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_deferred_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
-        d_genomes, d_sinv, num_genes, d_pairs, dlist, dcount, d_out, stride)));
-  } else if (small_fits(num_genes, false)) {
-    Launch L;
-    grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept, 8);
-    L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
-    GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
-    if (!rc && L.grid < npairs) {            // more pairs than resident blocks: throughput shape
-      grsr::pick_shape(num_genes, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
-      L.smem = grsr::work_bytes(num_genes, L.threads * L.ept, false) + grsr::stage_bytes(num_genes);
-      GRSR_DISPATCH_SHAPE(L.threads, L.ept, rc = finish_plan(grsr::dist_pairs_kernel<kNt, kEpt>, npairs, L));
-    }
-    if (rc) return rc;
-    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::dist_pairs_kernel<kNt, kEpt><<<L.grid, L.threads, L.smem, (cudaStream_t)stream>>>(
-        d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride)));
-  } else {
-    int dev;
-    CK(cudaGetDevice(&dev));
-    LargePlan LP;
-    rc = plan_large(grsr::dist_pairs_large_kernel, grsr::dist_pairs_cluster_kernel, npairs,
-                    grsr::large_work_bytes(num_genes, false), dev, LP);
-    if (rc) return rc;
-    if (LP.cs == 1) {
-      grsr::dist_pairs_large_kernel<<<LP.grid, 1024, 0, (cudaStream_t)stream>>>(
-          d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride, (unsigned char *)LP.scratch);
-    } else {
-      rc = launch_cluster(grsr::dist_pairs_cluster_kernel, LP, (cudaStream_t)stream, d_genomes, d_sinv,
-                          num_genes, d_pairs, (long long)npairs, d_out, stride,
-                          (unsigned char *)LP.scratch, (unsigned long long *)LP.xch);
-      if (rc) return rc;
-    }
-  }
-  CK(cudaGetLastError());
-  return GRSR_OK;
+  return dist_pairs_dev_impl(d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride,
+                             (cudaStream_t)stream, -1);
+}
+
+int grsr_dist_pairs_sorted_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
+                               const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
+                               void *stream) {
+  if (stride != 1 && stride != 5) return fail(GRSR_ERR_INVALID, "stride must be 1 or 5");
+  return dist_pairs_dev_impl(d_genomes, d_sinv, num_genes, d_pairs, npairs, d_out, stride,
+                             (cudaStream_t)stream, 1);
 }
 
 int grsr_dist_pairs(const int32_t *genomes, int num_genomes, int num_genes, const int32_t *pairs,
@@ -755,7 +992,9 @@ int grsr_dist_pairs(const int32_t *genomes, int num_genomes, int num_genes, cons
     if (pairs[p] < 0 || pairs[p] >= num_genomes)
       return fail(GRSR_ERR_INVALID, "pair %lld names genome %d of %d", (long long)(p / 2),
                   pairs[p], num_genomes);
-  if (npairs == 0) return GRSR_OK;
+  // an empty job still rejects a table that is not made of signed permutations (check_genes)
+  if (npairs == 0) return check_genomes(genomes, num_genomes, num_genes);
+  DeviceGuard guard;
   return shard_pairs(genomes, num_genomes, num_genes, PAIRS_LIST, pairs, npairs, out, stride,
                      first_device, ngpus);
 }
@@ -770,8 +1009,10 @@ int grsr_dist_matrix_shard(const int32_t *genomes, int num_genomes, int num_gene
   long long P = (long long)num_genomes * (num_genomes - 1) / 2;
   long long lo = P * shard / num_shards, hi = P * (shard + 1) / num_shards;
   *count = hi - lo;
+  if (hi == lo) return check_genomes(genomes, num_genomes, num_genes);
+  DeviceGuard guard;
   return run_pairs_on_device(device, genomes, num_genomes, num_genes, PAIRS_TRIANGLE, nullptr, lo,
-                             hi - lo, out, 1);
+                             hi - lo, out, 1, nullptr);
 }
 
 int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes, int32_t *distmatrix,
@@ -780,21 +1021,12 @@ int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes, int
   if (rc) return rc;
   if (!distmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
   if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
-  long long G = num_genomes, P = G * (G - 1) / 2;
-  std::vector<int32_t> flat((size_t)(P > 0 ? P : 1));
-  if (P > 0) {
-    rc = shard_pairs(genomes, num_genomes, num_genes, PAIRS_TRIANGLE, nullptr, P, flat.data(), 1,
-                     first_device, ngpus);
-    if (rc) return rc;
+  if (num_genomes == 1) {
+    distmatrix[0] = 0;
+    return check_genomes(genomes, num_genomes, num_genes);
   }
-  // host gather of matrix rows: distmatrix[i][j] = distmatrix[j][i] (G/uniinvdist.c:84-88)
-  long long p = 0;
-  for (long long j = 0; j < G; j++) {
-    distmatrix[j * G + j] = 0;
-    for (long long i = 0; i < j; i++, p++)
-      distmatrix[i * G + j] = distmatrix[j * G + i] = flat[p];
-  }
-  return GRSR_OK;
+  DeviceGuard guard;
+  return matrix_on_devices(genomes, num_genomes, num_genes, distmatrix, first_device, ngpus);
 }
 
 int grsr_stats_matrix(const int32_t *genomes, int num_genomes, int num_genes,
@@ -804,6 +1036,7 @@ int grsr_stats_matrix(const int32_t *genomes, int num_genomes, int num_genes,
   if (!statsmatrix) return fail(GRSR_ERR_INVALID, "null matrix");
   if ((rc = check_table(genomes, num_genomes, num_genes))) return rc;
   long long total = (long long)num_genomes * num_genomes;
+  DeviceGuard guard;
   return shard_pairs(genomes, num_genomes, num_genes, PAIRS_SQUARE, nullptr, total,
                      (int32_t *)statsmatrix, 5, first_device, ngpus);
 }
@@ -824,10 +1057,11 @@ int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes, 
   grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
   L.smem = grsr::work_bytes(n, L.threads * L.ept, false) + 2 * grsr::scen_arr_bytes(n);
   if (n > grsr::kMaxSmemGenes || 2 * n + 2 > 32767 || L.threads * L.ept < 2 * n + 2 ||
-      L.smem > 227u * 1024u)
+      L.smem > smem_budget())
     return fail(GRSR_ERR_TOOLARGE, "num_genes=%d: candidate scoring keeps the graph on chip "
                 "(at most %d genes)", n, grsr_max_genes_on_chip(0));
   if (device < 0 || device >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", device);
+  DeviceGuard guard;
   CK(cudaSetDevice(device));
   DevCache &c = g_cache[device];
   std::lock_guard<std::recursive_mutex> lk(c.mu);
@@ -863,24 +1097,39 @@ int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int 
   if (npairs == 0) return GRSR_OK;
   if ((rc = check_genomes(src, npairs, num_genes))) return rc;
   if ((rc = check_genomes(dst, npairs, num_genes))) return rc;
-  std::vector<int> rcs(ngpus, 0);
-  std::vector<std::string> errs(ngpus);
-  auto work = [&](int d) {
-    long long lo = (long long)npairs * d / ngpus, hi = (long long)npairs * (d + 1) / ngpus;
-    rcs[d] = scenario_on_device(first_device + d, src + lo * num_genes, dst + lo * num_genes,
-                                      (int)(hi - lo), num_genes, steps + lo * max_steps,
-                                      nsteps + lo, max_steps);
-    if (rcs[d]) errs[d] = g_err;
-  };
-  if (ngpus == 1) work(0);
-  else {
-    std::vector<std::thread> th;
-    for (int d = 0; d < ngpus; d++) th.emplace_back(work, d);
-    for (auto &t : th) t.join();
+  DeviceGuard guard;
+  return scenario_call(src, dst, npairs, num_genes, steps, nsteps, max_steps, nullptr, nullptr, false,
+                       first_device, ngpus);
+}
+
+int grsr_scenario_prefix(const int32_t *src, const int32_t *dst, int npairs, int num_genes,
+                         grsr_step_t *steps, int32_t *nsteps, int max_steps, int32_t *complete,
+                         int64_t *evals, int first_device, int ngpus) {
+  int rc = check_device_range(first_device, ngpus);
+  if (rc) return rc;
+  if (npairs < 0 || max_steps < 0 || (npairs > 0 && (!steps || !nsteps)))
+    return fail(GRSR_ERR_INVALID, "bad scenario arguments");
+  if (npairs == 0) return GRSR_OK;
+  if ((rc = check_genomes(src, npairs, num_genes))) return rc;
+  if ((rc = check_genomes(dst, npairs, num_genes))) return rc;
+  DeviceGuard guard;
+  return scenario_call(src, dst, npairs, num_genes, steps, nsteps, max_steps, complete, evals, true,
+                       first_device, ngpus);
+}
+
+#ifdef GRSR_PHASE_PROFILE
+/* diagnostic build only (scripts/prof_phases.py): cycles and entry counts per phase id */
+int grsr_prof_read(unsigned long long *cycles64, unsigned long long *counts64, int reset) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(cycles64, grsr::grsr_prof_cycles, 64 * sizeof(unsigned long long)));
+  CK(cudaMemcpyFromSymbol(counts64, grsr::grsr_prof_counts, 64 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    CK(cudaMemcpyToSymbol(grsr::grsr_prof_cycles, z, sizeof z));
+    CK(cudaMemcpyToSymbol(grsr::grsr_prof_counts, z, sizeof z));
   }
-  for (int d = 0; d < ngpus; d++)
-    if (rcs[d]) return fail(rcs[d], "device %d: %s", first_device + d, errs[d].c_str());
   return GRSR_OK;
 }
+#endif
 
 } // extern "C"

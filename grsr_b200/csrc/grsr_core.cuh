@@ -69,6 +69,54 @@ static const int kMaxSmemGenes = 14000;   // 2n+2 <= 32767 and ~10 B per vertex 
 
 struct Stats { int d, b, c, h, f; };
 
+// ---- phase timers (diagnostic build only: -DGRSR_PHASE_PROFILE, scripts/prof_phases.py) ------------
+// Thread 0 of every block charges the cycles since the previous mark to the phase that was running.
+// Phase ids: see scripts/prof_phases.py.  In the product build the marks compile to nothing.
+#if defined(GRSR_PHASE_PROFILE) && !defined(GRSR_EMU)
+__device__ unsigned long long grsr_prof_cycles[64];
+__device__ unsigned long long grsr_prof_counts[64];
+struct PhaseState { long long last; int cur; int base; };
+__device__ inline PhaseState &phase_state() { __shared__ PhaseState ps; return ps; }
+__device__ inline void phase_init() {
+  if (threadIdx.x == 0) { PhaseState &ps = phase_state(); ps.last = clock64(); ps.cur = 0; ps.base = 0; }
+}
+__device__ inline void phase_mark(int id) {
+  if (threadIdx.x == 0) {
+    PhaseState &ps = phase_state();
+    const long long t = clock64();
+    atomicAdd(&grsr_prof_cycles[ps.cur], (unsigned long long)(t - ps.last));
+    atomicAdd(&grsr_prof_counts[id], 1ull);
+    ps.last = t; ps.cur = id;
+  }
+}
+__device__ inline void phase_base(int b) { if (threadIdx.x == 0) phase_state().base = b; }
+__device__ inline void phase_mark_rel(int k) { if (threadIdx.x == 0) phase_mark(phase_state().base + k); }
+#define GRSR_PHASE_INIT() phase_init()
+#define GRSR_PHASE(id) phase_mark(id)
+#define GRSR_PHASE_BASE(b) phase_base(b)
+#define GRSR_PHASE_REL(k) phase_mark_rel(k)
+#else
+#define GRSR_PHASE_INIT() ((void)0)
+#define GRSR_PHASE(id) ((void)0)
+#define GRSR_PHASE_BASE(b) ((void)0)
+#define GRSR_PHASE_REL(k) ((void)0)
+#endif
+
+// Where the result of pair p = (gamma row gi, pi row pj) goes.  stride 1: out[p] = d; stride 5:
+// out + 5p = {d,b,c,h,f}; stride -G (matrix mode): the symmetric scatter of setinvmatrix
+// (G/uniinvdist.c:84-88) done by the kernel itself, out[gi*G + pj] = out[pj*G + gi] = d -- `out` may
+// then be a matrix in ANOTHER device's memory (peer mapping over NVLink): 8 bytes per pair.
+__device__ inline void put_result(int32_t *__restrict__ out, int stride, long long p, int gi, int pj,
+                                  int d, int b, int c, int h, int f) {
+  if (stride == 1) out[p] = d;
+  else if (stride == 5) { int32_t *o = out + 5 * p; o[0] = d; o[1] = b; o[2] = c; o[3] = h; o[4] = f; }
+  else {
+    const long long G = -stride;
+    out[(long long)gi * G + pj] = d;
+    out[(long long)pj * G + gi] = d;
+  }
+}
+
 template <class VT> __host__ __device__ constexpr unsigned none_of() { return (unsigned)(VT)(~(VT)0); }
 
 // Workspace of one pair.  S = 2n+2 vertices.  VT = vertex id type: uint16_t when the graph lives in
@@ -306,6 +354,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   uint32_t *W = wk.P; VT *A1 = wk.A1, *A2 = wk.A2, *BLK = wk.BLK;
   VT *bmin = BLK, *bmax = BLK + wk.NB;
 
+  GRSR_PHASE(20);
   // S1: start the union-find forest (W[r] = r) and the reach (W[r+1] = rightmost vertex of
   //     cycle r, filled by S2).
   for (int k = tid; k <= n; k += nt) {
@@ -314,6 +363,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
+  GRSR_PHASE(21);
   // S2: reach of every cycle = max vertex carrying its id (reference: right[], G/graph_edit.c:392).
   //     Lanes hold consecutive vertices, so the highest lane of each equal-id group carries the max.
   for (int base = tid & ~31; base < S; base += nt) {
@@ -324,6 +374,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
+  GRSR_PHASE(22);
   // S3: per block of 32 vertices: smallest cycle id and largest reach seen in it.
   for (int B = tid; B < wk.NB; B += nt) {
     unsigned mn = kNone, mx = 0;
@@ -338,6 +389,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
+  GRSR_PHASE(23);
   // S4: for every cycle P = (l, r): among the vertices strictly inside (l, r), the smallest cycle id
   //     (a cycle that starts left of P and reaches into it) and the largest reach (a cycle that
   //     reaches into P and ends right of it).  Those two neighbours are enough to recover the
@@ -397,6 +449,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
+  GRSR_PHASE(24);
   // S5: connected components of the cycles under those links: hook larger root under smaller,
   //     compress, repeat until no link joins two trees.
   for (;;) {
@@ -424,6 +477,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     TM::sync();
   }
 
+  GRSR_PHASE(25);
   // S6: a component is oriented iff one of its cycles is (G/graph_components.c:309-336).
   //     W[c+1] of the component root c becomes that flag (the reach is no longer needed).
   for (int k = tid; k <= n; k += nt) {
@@ -437,6 +491,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
+  GRSR_PHASE(26);
   // S7: the vertices of unoriented components, in vertex order, as a list of component ids
   //     (the filtered scan of G/graph_components.c:566-585).
   int m = TM::compact(S, [&](int v, unsigned &val) -> bool {
@@ -448,6 +503,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }, A1, wk);
   if (m == 0) return 0;
 
+  GRSR_PHASE(27);
   // S8: runs of equal ids = the reference's "blocks"; keep one entry per run.
   int nb = TM::compact(m, [&](int t, unsigned &val) -> bool {
     unsigned c = A1[t];
@@ -456,6 +512,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }, A2, wk);
   const VT *run = A2;
 
+  GRSR_PHASE(28);
   // S9: per component: number of runs (W[c]) and 1 + index of its last run (W[c+1]).
   for (int t = tid; t < nb; t += nt) { unsigned c = run[t]; W[c] = 0; W[c + 1] = 0; }
   TM::sync();
@@ -586,6 +643,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   // (G/mcrdist.c:135-140) and oriented when x and y have the same parity
   // (G/graph_components.c:324-329).
   unsigned nadj = 0;
+  GRSR_PHASE_REL(0);
   {
     const int per = ((((n + 1) + (NT >> 5) - 1) / (NT >> 5)) + 31) & ~31;
     const int t0 = wid * per;
@@ -616,6 +674,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   // successors; stop after ceil(log2(n+1)) rounds or as soon as a whole round changed no label and
   // no flag.  A thread keeps its EPT words in registers; per round it gathers the words of its
   // successors (in batches, loads before stores), merges and publishes.
+  GRSR_PHASE_REL(1);
   {
     constexpr int UB = (EPT < 8) ? EPT : 8;
     uint32_t R[EPT];
@@ -649,6 +708,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   // orbit labels; the edge whose left end is its own cycle id is the cycle's root -> count cycles
   // and the roots whose orbit saw no oriented grey edge.
   unsigned ncyc = 0, nun = 0;
+  GRSR_PHASE_REL(2);
   for (int k = tid; k <= n; k += NT) {
     const unsigned a = 2u * k;
     const uint2 ww = *(const uint2 *)(W + a);
@@ -672,6 +732,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
       })) {
     // some unoriented cycle is not obviously covered: the component analysis is needed.  Cycle
     // id per vertex and the orientation flag of every cycle first.
+    GRSR_PHASE_REL(3);
     uint32_t *A2w = (uint32_t *)wk.A2;
     for (int k = tid; k <= n; k += NT) {
       const unsigned a = 2u * k;
@@ -684,6 +745,7 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
     unsigned hf = hurdles_slow_path<TeamBlock>(wk, n);
     st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
   }
+  GRSR_PHASE(0);
   st.d = st.b - st.c + st.h + st.f;
   return st;
 }
@@ -922,6 +984,7 @@ dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, false);
+  GRSR_PHASE_INIT(); GRSR_PHASE_BASE(8);
   uint16_t *stage = (uint16_t *)(smem_raw + work_bytes(n, NT * EPT, false));
   const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
   const long long p0 = (long long)blockIdx.x * chunk;
@@ -940,10 +1003,7 @@ dist_pairs_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict
     }
     EndsFromRows ends; ends.gamma = genomes + (long long)gi * n; ends.tail = stage;
     Stats st = dist_core<NT, EPT, false>(wk, n, ends);
-    if (threadIdx.x == 0) {
-      if (stride == 1) out[p] = st.d;
-      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
-    }
+    if (threadIdx.x == 0) put_result(out, stride, p, gi, pj, st.d, st.b, st.c, st.h, st.f);
   }
 }
 
@@ -971,10 +1031,8 @@ dist_pairs_large_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
     ends.gamma = genomes + (long long)pairs[2 * p] * n;
     ends.sinv_pi = sinv + (long long)pairs[2 * p + 1] * n;
     Stats st = dist_core_large<TeamBlock, false>(wk, n, ends);
-    if (threadIdx.x == 0) {
-      if (stride == 1) out[p] = st.d;
-      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
-    }
+    if (threadIdx.x == 0)
+      put_result(out, stride, p, pairs[2 * p], pairs[2 * p + 1], st.d, st.b, st.c, st.h, st.f);
   }
 }
 

@@ -84,6 +84,18 @@ struct EndsTrial {
   }
 };
 
+// The pair ticket may live in ANOTHER device's memory (several GPUs drawing pairs from one queue over
+// NVLink peer mapping): system-scope atomic.
+#ifdef GRSR_EMU
+__device__ inline unsigned ticket_next(unsigned int *ticket) { return atomicAdd(ticket, 1u); }
+#else
+__device__ inline unsigned ticket_next(unsigned int *ticket) { return atomicAdd_system(ticket, 1u); }
+#endif
+
+// How a launch maps tickets to pairs: pair = first + ticket * stride.  One queue shared by all
+// devices: (0, 1); device k of g without peer access: (k, g) with a private ticket.
+struct PairQueue { unsigned int *ticket; int first, stride; };
+
 #define GRSR_SCEN_OK        0
 #define GRSR_SCEN_OVERFLOW  1   /* more steps than max_steps */
 #define GRSR_SCEN_STUCK     2   /* no candidate reduces the distance (reference: S_FAIL) */
@@ -122,7 +134,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
                                      int npairs, int n, int32_t *__restrict__ steps,
                                      int32_t *__restrict__ nsteps, int max_steps,
                                      int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                                     unsigned int *ticket, volatile int *s_pair, volatile unsigned *bound,
+                                     PairQueue queue, volatile int *s_pair, volatile unsigned *bound,
                                      int resume = 0) {
   typedef typename Pol::sval SV;
   typedef typename Pol::vid VT;
@@ -131,9 +143,13 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
   const unsigned long long kNoKey = ~0ull;
   const VT *ORB = wk.ORB;
   const int tid = TM::tid(), nt = TM::size();
+  GRSR_PHASE_INIT();
 
   for (;;) {
-    if (tid == 0) *s_pair = (int)atomicAdd(ticket, 1u);
+    if (tid == 0) {
+      const long long q = (long long)queue.first + (long long)ticket_next(queue.ticket) * queue.stride;
+      *s_pair = (q < npairs) ? (int)q : npairs;
+    }
     TM::sync();
     const int p = *s_pair;
     TM::sync();
@@ -147,11 +163,15 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
     }
     TM::sync();
 
-    int ns = resume ? nsteps[p] : 0, code = GRSR_SCEN_OK;   // resume: steps [0, nsteps[p]) already written
-    unsigned long long nevals = 0;
+    // resume: steps [0, nsteps[p]) were written (and evals[p] evaluations made) by the stepwise path;
+    // a pair it ended (step limit reached, search stuck) is left as it is
+    if (resume && status[p] != GRSR_SCEN_OK) continue;
+    int ns = resume ? nsteps[p] : 0, code = GRSR_SCEN_OK;
+    unsigned long long nevals = (resume && evals) ? evals[p] : 0ull;
     for (;;) {
       // rho0 (signed position in the destination of the gene at position i of the current genome)
       // and its inverse: G0 and every trial of this step are written from these two arrays
+      GRSR_PHASE(1);
       for (int i = tid; i < n; i += nt) {
         int g = CUR[i];
         int s = SDST[(g > 0 ? g : -g) - 1];
@@ -161,7 +181,9 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
       }
       TM::sync();
       EndsG0<SV> eg; eg.inv0 = INV0;
+      GRSR_PHASE_BASE(2);
       const Stats g0 = Pol::template dist<true>(wk, n, eg);   // G/opt_scenario.c:229
+      GRSR_PHASE(6);
       if (g0.d == 0) break;
       if (ns >= max_steps) { code = GRSR_SCEN_OVERFLOW; break; }
 
@@ -179,6 +201,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
       // whose orbit partner is far away stops scanning as soon as somebody has a shorter candidate
       for (;;) {
         // smallest key (j - i, i) greater than lastkey among admissible candidates
+        GRSR_PHASE(7);
         if (tid == 0) *bound = 0xFFFFFFFFu;
         TM::sync();
         unsigned long long best = kNoKey;
@@ -215,6 +238,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
         const int i = (int)(best & 0xFFFFFFFFull);
         const int j = i + (int)(best >> 32);
         EndsTrial<SV> et; et.rho0 = RHO0; et.i = i; et.j = j;
+        GRSR_PHASE_BASE(8);
         const Stats t1 = Pol::template dist<false>(wk, n, et);  // G/opt_scenario.c:974-986
         nevals++;
         if (t1.d == g0.d - 1) { fi = i; fj = j; break; }
@@ -223,6 +247,7 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
       if (fi < 0) { code = GRSR_SCEN_STUCK; break; }
 
       // current <- trial (G/opt_scenario.c:283-285)
+      GRSR_PHASE(13);
       for (int k = tid; 2 * k <= fj - fi; k += nt) {
         int a = fi + k, b = fj - k;
         SV x = CUR[a], y = CUR[b];
@@ -251,10 +276,11 @@ __global__ void __launch_bounds__(NT, GRSR_MIN_BLOCKS(NT, EPT))
 scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                 int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                 int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                unsigned int *ticket, int resume) {
+                PairQueue queue, int resume) {
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, true);
+  GRSR_PHASE_INIT(); GRSR_PHASE_BASE(8);
   unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, true);
   int16_t *CUR = (int16_t *)extra;
   int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
@@ -263,7 +289,7 @@ scenario_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst
   uint16_t *BPL = (uint16_t *)(extra + 4 * scen_arr_bytes(n));
   __shared__ int s_pair;
   scenario_body<ScenSmall<NT, EPT> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
-                                     max_steps, status, evals, ticket, &s_pair,
+                                     max_steps, status, evals, queue, &s_pair,
                                      (volatile unsigned *)&wk.red[33], resume);
 }
 
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(1024)
 scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                       int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                       int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                      unsigned int *ticket, unsigned char *scratch) {
+                      PairQueue queue, unsigned char *scratch) {
   __shared__ unsigned long long red[34];
   __shared__ int s_pair;
   unsigned char *base = scratch + (size_t)blockIdx.x * scen_large_bytes(n);
@@ -290,7 +316,7 @@ scenario_large_kernel(const int32_t *__restrict__ src, const int32_t *__restrict
   int32_t *RHO0 = (int32_t *)(extra + 3 * scen_large_arr_bytes(n));
   uint32_t *BPL = (uint32_t *)(extra + 4 * scen_large_arr_bytes(n));
   scenario_body<ScenLarge<TeamBlock> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
-                                       max_steps, status, evals, ticket, &s_pair,
+                                       max_steps, status, evals, queue, &s_pair,
                                        (volatile unsigned *)&red[33]);
 }
 
@@ -307,6 +333,7 @@ trial_batch_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ 
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, false);
+  GRSR_PHASE_INIT(); GRSR_PHASE_BASE(8);
   unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, false);
   int16_t *SDST = (int16_t *)extra;
   int16_t *RHO0 = (int16_t *)(extra + scen_arr_bytes(n));
@@ -338,7 +365,7 @@ __global__ void __launch_bounds__(1024)
 scenario_cluster_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ dst, int npairs, int n,
                         int32_t *__restrict__ steps, int32_t *__restrict__ nsteps, int max_steps,
                         int32_t *__restrict__ status, unsigned long long *__restrict__ evals,
-                        unsigned int *ticket, unsigned char *scratch, unsigned long long *xch_all) {
+                        PairQueue queue, unsigned char *scratch, unsigned long long *xch_all) {
   GRSR_DYN_SMEM(smem_raw);
   unsigned long long *red = (unsigned long long *)smem_raw;
   const unsigned cid = blockIdx.x / cluster_size();
@@ -354,7 +381,7 @@ scenario_cluster_kernel(const int32_t *__restrict__ src, const int32_t *__restri
   int32_t *RHO0 = (int32_t *)(extra + 3 * scen_large_arr_bytes(n));
   uint32_t *BPL = (uint32_t *)(extra + 4 * scen_large_arr_bytes(n));
   scenario_body<ScenLarge<TeamCluster> >(wk, CUR, SDST, INV0, RHO0, BPL, src, dst, npairs, n, steps, nsteps,
-                                         max_steps, status, evals, ticket,
+                                         max_steps, status, evals, queue,
                                          (volatile int *)(xch + kXchWords - 4),
                                          (volatile unsigned *)(xch + kXchWords - 2));
 }
@@ -376,10 +403,8 @@ dist_pairs_cluster_kernel(const int32_t *__restrict__ genomes, const int32_t *__
     ends.gamma = genomes + (long long)pairs[2 * p] * n;
     ends.sinv_pi = sinv + (long long)pairs[2 * p + 1] * n;
     Stats st = dist_core_large<TeamCluster, false>(wk, n, ends);
-    if (TeamCluster::tid() == 0) {
-      if (stride == 1) out[p] = st.d;
-      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
-    }
+    if (TeamCluster::tid() == 0)
+      put_result(out, stride, p, pairs[2 * p], pairs[2 * p + 1], st.d, st.b, st.c, st.h, st.f);
   }
 }
 

@@ -29,6 +29,7 @@ struct StepState {
   int32_t status;                  // GRSR_SCEN_*
   unsigned long long lastkey;      // every candidate with key <= lastkey of this step has been rejected
   unsigned long long batch_end;    // largest key of the current batch
+  unsigned long long evals;        // full trial evaluations made so far (whole batches are scored)
 };
 
 // One block.  cur/dst: the pair (global, int32).  cands: capacity cap pairs (i, j).
@@ -39,6 +40,7 @@ step_prepare_kernel(const int32_t *__restrict__ cur, const int32_t *__restrict__
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, true);
+  GRSR_PHASE_INIT(); GRSR_PHASE_BASE(8);
   unsigned char *extra = smem_raw + work_bytes(n, NT * EPT, true);
   int16_t *CUR = (int16_t *)extra;
   int16_t *SDST = (int16_t *)(extra + scen_arr_bytes(n));
@@ -74,7 +76,9 @@ step_prepare_kernel(const int32_t *__restrict__ cur, const int32_t *__restrict__
   }, BPL, wk.red);
   const unsigned long long lastkey = st->lastkey;
   const int g_last = (lastkey == kNoKey) ? -1 : (int)(lastkey >> 32);
-  const int i_last = (lastkey == kNoKey) ? -1 : (int)(lastkey & 0xFFFFFFFFull);
+  // low word 0xFFFFFFFF = "the whole diagonal g_last has been scored" (batch_end of a hurdle batch):
+  // it must compare greater than every position, so it stays unsigned in a 64-bit integer
+  const long long i_last = (lastkey == kNoKey) ? -1ll : (long long)(lastkey & 0xFFFFFFFFull);
   __syncthreads();
 
   int ncand = 0;
@@ -171,6 +175,7 @@ step_select_kernel(int32_t *cur, int n, StepState *st, const int32_t *__restrict
   const int tid = threadIdx.x;
   const int ncand = st->ncand, d = st->d;
   if (d == 0) return;
+  if (tid == 0) st->evals += (unsigned long long)ncand;
   unsigned long long best = ~0ull;
   for (int c = tid; c < ncand; c += blockDim.x) {
     if (d2[c] == d - 1) {

@@ -210,7 +210,7 @@ __device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
 // One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
 // in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
 __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
-                                 long long p, int32_t *__restrict__ out, int stride, int shape,
+                                 int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
                                  int32_t *defer_list, unsigned *defer_count) {
   const int shift = shape & 0xFF, idle_min = shape >> 8;   // node stride 2^shift; lanes out of work before new walks start
   const int lane = threadIdx.x & 31;
@@ -460,13 +460,8 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   }
 
   if (lane == 0) {
-    if (defer) {
-      defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
-    } else if (stride == 1) {
-      out[p] = b - c;
-    } else {
-      int32_t *o = out + 5 * p; o[0] = b - c; o[1] = b; o[2] = c; o[3] = 0; o[4] = 0;
-    }
+    if (defer) defer_list[atomicAdd(defer_count, 1u)] = (int32_t)p;
+    else put_result(out, stride, p, gi, pj, b - c, b, c, 0, 0);
   }
   __syncwarp();
   return defer != 0;
@@ -490,14 +485,22 @@ __device__ inline bool walk_list_sorted(const unsigned *changes, long long npair
   return (unsigned long long)*changes * 64ull <= (unsigned long long)npairs;
 }
 
-// One warp, one pair at a time, every warp with its own staged pi row: warp w of the launch owns the
-// contiguous pairs [w * chunk, (w+1) * chunk); tail[] stays staged while consecutive pairs share
-// their pi row.  Serves pair lists in any order.
+// Work distribution of both kernels: a zero-initialised global ticket hands out chunks of
+// consecutive pairs, so a warp (block) that drew cheap pairs simply draws more -- no static split
+// whose slowest part the launch has to wait for.  chunk = pairs per ticket (>= 1).
+__host__ __device__ inline int walk_chunk(long long npairs, long long takers, int lo, int hi) {
+  long long c = npairs / (takers * 8);                // about 8 tickets per taker
+  return (int)(c < lo ? lo : (c > hi ? hi : c));
+}
+
+// One warp, one pair at a time, every warp with its own staged pi row: a warp draws chunks of
+// consecutive pairs from the ticket; tail[] stays staged while consecutive pairs share their pi row.
+// Serves pair lists in any order.
 __global__ void __launch_bounds__(256)
 dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                  const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                  int stride, int shape, int32_t *defer_list, unsigned *defer_count,
-                 const unsigned *__restrict__ order_flag) {
+                 const unsigned *__restrict__ order_flag, unsigned *ticket) {
   if (order_flag && walk_list_sorted(order_flag, npairs)) return;   // pi-sorted list: the shared-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -510,40 +513,46 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   if (lane == 0) tail[n] = (uint16_t)(2 * n + 1);     // the sentinel gene's entry
   __syncwarp();
 
-  const long long nwarps = (long long)gridDim.x * wpb;
-  const long long chunk = (npairs + nwarps - 1) / nwarps;
-  const long long p0 = ((long long)blockIdx.x * wpb + wid) * chunk;
-  const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
+  const int chunk = walk_chunk(npairs, (long long)gridDim.x * wpb, 1, 8);
   int staged = -1;
   WalkQuota quota = {0, 0};
-  for (long long p = p0; p < p1; p++) {
-    if (quota.gave_up()) { walk_defer_unseen(p, defer_list, defer_count); continue; }
-    const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
-    if (pj != staged) {
-      const int32_t *sp = sinv + (long long)pj * n;
-      for (int i = lane; i < n; i += 32) {
-        const int s = sp[i];
-        tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
+  for (;;) {
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    const long long p0 = (long long)t * chunk;
+    if (p0 >= npairs) break;
+    const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
+    for (long long p = p0; p < p1; p++) {
+      if (quota.gave_up()) { walk_defer_unseen(p, defer_list, defer_count); continue; }
+      const int gi = pairs[2 * p], pj = pairs[2 * p + 1];
+      if (pj != staged) {
+        const int32_t *sp = sinv + (long long)pj * n;
+        for (int i = lane; i < n; i += 32) {
+          const int s = sp[i];
+          tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
+        }
+        staged = pj;
+        __syncwarp();
       }
-      staged = pj;
-      __syncwarp();
+      quota.count(walk_pair(wm, genomes, n, gi, pj, p, out, stride, shape, defer_list, defer_count));
     }
-    quota.count(walk_pair(wm, genomes, n, gi, p, out, stride, shape, defer_list, defer_count));
   }
 }
 
 // The same for pair lists sorted by pi row (the column-by-column triangle of a distance matrix): the
 // warps of a block share ONE staged pi row, which leaves room for more resident warps per SM.  A block
-// owns a contiguous chunk of the list and goes through it one run of equal pi rows at a time.
+// draws chunks of consecutive pairs from the ticket and goes through a chunk one run of equal pi rows
+// at a time; inside a run its warps take pairs from a shared-memory counter, one at a time.
 __global__ void __launch_bounds__(1024)
 dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict__ sinv, int n,
                         const int32_t *__restrict__ pairs, long long npairs, int32_t *__restrict__ out,
                         int stride, int shape, int32_t *defer_list, unsigned *defer_count,
-                        const unsigned *__restrict__ order_flag) {
+                        const unsigned *__restrict__ order_flag, unsigned *ticket) {
   if (order_flag && !walk_list_sorted(order_flag, npairs)) return;  // not sorted: the private-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  unsigned *s_end = (unsigned *)smem_raw;             // first 16 bytes: run length found by the block
+  unsigned *s_ctl = (unsigned *)smem_raw;             // first 16 bytes: [0] run length, [1] next pair of the run, [2] ticket
   uint16_t *tail = (uint16_t *)(smem_raw + 16);
   WalkMem wm;
   wm.tail = tail;
@@ -552,33 +561,48 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n + 1);
 
   WalkQuota quota = {0, 0};
-  const long long chunk = (npairs + gridDim.x - 1) / gridDim.x;
-  const long long b0 = (long long)blockIdx.x * chunk;
-  const long long b1 = (b0 + chunk < npairs) ? b0 + chunk : npairs;
-  for (long long p = b0; p < b1;) {
-    const int pj = pairs[2 * p + 1];
-    const unsigned left = (unsigned)(b1 - p);
-    __syncthreads();                                   // everybody is done with the previous run
-    if (threadIdx.x == 0) *s_end = left;
+  const int chunk = walk_chunk(npairs, gridDim.x, wpb, 8 * wpb);
+  int staged = -1;
+  for (;;) {
+    __syncthreads();                                   // everybody is done with the previous chunk
+    if (threadIdx.x == 0) s_ctl[2] = atomicAdd(ticket, 1u);
     __syncthreads();
-    for (unsigned qb = 0; qb < left; qb += blockDim.x) {
-      const unsigned q = qb + threadIdx.x;
-      const bool diff = q < left && pairs[2 * (p + q) + 1] != pj;
-      if (diff) atomicMin(s_end, q);
-      if (__syncthreads_or(diff)) break;
+    const long long b0 = (long long)s_ctl[2] * chunk;
+    if (b0 >= npairs) break;
+    const long long b1 = (b0 + chunk < npairs) ? b0 + chunk : npairs;
+    for (long long p = b0; p < b1;) {
+      const int pj = pairs[2 * p + 1];
+      const unsigned left = (unsigned)(b1 - p);
+      __syncthreads();                                 // everybody is done with the previous run
+      if (threadIdx.x == 0) { s_ctl[0] = left; s_ctl[1] = 0; }
+      __syncthreads();
+      for (unsigned qb = 0; qb < left; qb += blockDim.x) {
+        const unsigned q = qb + threadIdx.x;
+        const bool diff = q < left && pairs[2 * (p + q) + 1] != pj;
+        if (diff) atomicMin(&s_ctl[0], q);
+        if (__syncthreads_or(diff)) break;
+      }
+      if (pj != staged) {
+        const int32_t *sp = sinv + (long long)pj * n;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          const int s = sp[i];
+          tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);
+        }
+        staged = pj;
+      }
+      __syncthreads();
+      const unsigned run = s_ctl[0];
+      for (;;) {
+        unsigned q = 0;
+        if (lane == 0) q = atomicAdd(&s_ctl[1], 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= run) break;
+        if (quota.gave_up()) { walk_defer_unseen(p + q, defer_list, defer_count); continue; }
+        quota.count(walk_pair(wm, genomes, n, pairs[2 * (p + q)], pj, p + q, out, stride, shape,
+                              defer_list, defer_count));
+      }
+      p += run;
     }
-    const int32_t *sp = sinv + (long long)pj * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int s = sp[i];
-      tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);
-    }
-    __syncthreads();
-    const unsigned run = *s_end;
-    for (unsigned q = wid; q < run; q += wpb) {
-      if (quota.gave_up()) { walk_defer_unseen(p + q, defer_list, defer_count); continue; }
-      quota.count(walk_pair(wm, genomes, n, pairs[2 * (p + q)], p + q, out, stride, shape, defer_list, defer_count));
-    }
-    p += run;
   }
 }
 
@@ -603,6 +627,7 @@ dist_deferred_kernel(const int32_t *__restrict__ genomes, const int32_t *__restr
   GRSR_DYN_SMEM(smem_raw);
   Work wk;
   work_carve(wk, smem_raw, n, NT * EPT, false);
+  GRSR_PHASE_INIT(); GRSR_PHASE_BASE(8);
   uint16_t *stage = (uint16_t *)(smem_raw + work_bytes(n, NT * EPT, false));
   const long long total = (long long)*defer_count;
   int staged = -1;
@@ -621,10 +646,7 @@ dist_deferred_kernel(const int32_t *__restrict__ genomes, const int32_t *__restr
     }
     EndsFromRows ends; ends.gamma = genomes + (long long)gi * n; ends.tail = stage;
     Stats st = dist_core<NT, EPT, false>(wk, n, ends);
-    if (threadIdx.x == 0) {
-      if (stride == 1) out[p] = st.d;
-      else { int32_t *o = out + 5 * p; o[0] = st.d; o[1] = st.b; o[2] = st.c; o[3] = st.h; o[4] = st.f; }
-    }
+    if (threadIdx.x == 0) put_result(out, stride, p, gi, pj, st.d, st.b, st.c, st.h, st.f);
   }
 }
 

@@ -74,7 +74,9 @@ int grsr_dist_pairs(const int32_t *genomes, int num_genomes, int num_genes,
                     int32_t *out, int stride, int first_device, int ngpus);
 
 /* setinvmatrix(distmatrix, genomes, num_genes, num_genomes, distmem, FALSE)  (G/uniinvdist.c:75-92):
- * distmatrix is num_genomes x num_genomes row-major; diagonal 0, [i][j] = [j][i] = d(g_i, g_j), i<j. */
+ * distmatrix is num_genomes x num_genomes row-major; diagonal 0, [i][j] = [j][i] = d(g_i, g_j), i<j.
+ * The kernels write both triangle halves of the matrix themselves (on ngpus > 1 devices into the
+ * first device's copy, through NVLink peer mappings); the host receives one finished matrix. */
 int grsr_dist_matrix(const int32_t *genomes, int num_genomes, int num_genes,
                      int32_t *distmatrix, int first_device, int ngpus);
 
@@ -99,6 +101,20 @@ int grsr_scenario_batch(const int32_t *src, const int32_t *dst, int npairs, int 
                         grsr_step_t *steps, int32_t *nsteps, int max_steps,
                         int first_device, int ngpus);
 
+/* The first max_steps steps of the same scenarios (the whole scenario where it is shorter): what
+ * print_scenario_2 has printed when it is stopped after max_steps "Step k:" lines.  A scenario is a
+ * sequential chain of steps, each costing up to O(n^2) full distance evaluations when hurdles are
+ * present (G/opt_scenario.c:951-986), so callers that sample, preview or time-box a batch bound the
+ * work per pair this way.  complete[p] (may be NULL) = 1 if pair p reached its destination;
+ * evals[p] (may be NULL) = number of full trial evaluations made for pair p.
+ *
+ * Both scenario calls shard over ngpus devices dynamically: all devices draw pairs from one queue
+ * (a ticket in the first device's memory, NVLink peer atomics), because per-pair work differs by
+ * orders of magnitude. */
+int grsr_scenario_prefix(const int32_t *src, const int32_t *dst, int npairs, int num_genes,
+                         grsr_step_t *steps, int32_t *nsteps, int max_steps, int32_t *complete,
+                         int64_t *evals, int first_device, int ngpus);
+
 /* Every listed candidate reversal of one pair scored at once -- the loop of print_rev_stats_t1
  * (G/testrev.c:156-215, `grimm -t 1`) and the evaluation of optrev_try_op (G/opt_scenario.c:974-986):
  * out[c] = invdist_noncircular(trial_c, dst) where trial_c = src with positions cands[2c] ..
@@ -108,9 +124,10 @@ int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes,
                          const int32_t *cands, int64_t ncand, int32_t *out, int device);
 
 /* ---- device-resident entry points (pointers are CUDA device pointers on the CURRENT device;
- *      stream is a cudaStream_t; no validation, no copies, asynchronous).  Beyond
- *      grsr_max_genes_on_chip() genes the kernels use a per-device workspace the library owns:
- *      keep at most one such call in flight per device. ------------------------------------------ */
+ *      stream is a cudaStream_t; no validation, no copies, asynchronous).  Up to
+ *      grsr_max_genes_on_chip() genes a call takes its scratch from the device's stream-ordered
+ *      memory pool, so calls on different streams are independent.  Beyond that the kernels use a
+ *      per-device workspace the library owns: keep at most one such call in flight per device. --- */
 
 /* signed inverse of every genome: d_sinv[g*n + |x|-1] = sign(x) * (position of x in genome g + 1) */
 int grsr_signed_inverse_dev(const int32_t *d_genomes, int num_genomes, int num_genes,
@@ -120,6 +137,13 @@ int grsr_signed_inverse_dev(const int32_t *d_genomes, int num_genomes, int num_g
 int grsr_dist_pairs_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
                         const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
                         void *stream);
+
+/* the same for a list the caller knows to be sorted by pi row (pairs[2p+1] non-decreasing in long
+ * runs, e.g. the output of grsr_triangle_pairs_dev): skips the order test on the device.  On any
+ * other list the results are still correct, only slower. */
+int grsr_dist_pairs_sorted_dev(const int32_t *d_genomes, const int32_t *d_sinv, int num_genes,
+                               const int32_t *d_pairs, int64_t npairs, int32_t *d_out, int stride,
+                               void *stream);
 
 /* fills d_pairs[2q], d_pairs[2q+1] with pair first+q of the column-by-column upper triangle */
 int grsr_triangle_pairs_dev(int num_genomes, int64_t first, int64_t count, int32_t *d_pairs,

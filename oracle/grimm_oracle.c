@@ -311,7 +311,20 @@ static void build_successors(const int *dst, int n, int *succ) {
 
 /* a14-a16: print_scenario_2 / try_optrev / optrev_try_op (G/opt_scenario.c:227-290, 527-576,
  * 951-986). */
+static int scenario_run(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals,
+                        int prefix);
+
 int orc_scenario(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals) {
+  return scenario_run(src, dst, n, steps, maxsteps, evals, 0);
+}
+
+/* the first maxsteps steps of the same scenario (all of it when it is shorter): returns their number */
+int orc_scenario_prefix(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals) {
+  return scenario_run(src, dst, n, steps, maxsteps, evals, 1);
+}
+
+static int scenario_run(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals,
+                        int prefix) {
   ws_t g0, wt;
   int *cur = xcalloc(n, sizeof(int)), *trial = xcalloc(n, sizeof(int));
   int *succ = xcalloc(2 * n + 3, sizeof(int));
@@ -325,6 +338,7 @@ int orc_scenario(const int *src, const int *dst, int n, int *steps, int maxsteps
     int len, i, j, k, found = 0;
     long nev = 0;
     if (d == 0) break;
+    if (prefix && nsteps >= maxsteps) break;
     for (len = 0; len < n && !found; len++) {
       for (i = 0; i + len < n; i++) {
         int *t;

@@ -50,6 +50,10 @@ int orc_graph(const int *gamma, const int *pi, int n, int *perm, int *grey, int 
  * If evals != NULL it receives the number of full distance evaluations made per step. */
 int orc_scenario(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals);
 
+/* The first maxsteps steps of that scenario (the whole of it when it is shorter); returns their
+ * number, -2 if the search fails. */
+int orc_scenario_prefix(const int *src, const int *dst, int n, int *steps, int maxsteps, long *evals);
+
 /* The inner loop of print_rev_stats_t1 (G/testrev.c:156-215): out[c] = invdist_noncircular(trial_c,
  * dst) with trial_c = src after copy_and_reverse_genes(cands[2c], cands[2c+1]). */
 void orc_trial_distances(const int *src, const int *dst, int n, const int *cands, long ncand, int *out);

@@ -113,3 +113,47 @@ int ref_scenario(const int *src, const int *dst, int n, int *steps, int maxsteps
   free(buf);
   return nsteps;
 }
+
+/* The first `cap` steps of the reference's scenario (all of it when it is shorter).  print_scenario_2
+ * has no step limit, so it runs in a forked child that prints into a pipe; the parent parses the
+ * "Step k:" lines as they arrive and kills the child once it has `cap` of them.  This is how the
+ * n = 100000 pair of config 5 (days of CPU for the whole scenario) and hurdle-rich n = 5000 pairs
+ * (minutes per pair) get reference step prefixes.  Returns the number of steps read. */
+#include <unistd.h>
+#include <signal.h>
+#include <sys/wait.h>
+int ref_scenario_prefix(const int *src, const int *dst, int n, int *steps, int cap)
+{
+  int fd[2], nsteps = 0;
+  pid_t pid;
+  FILE *in;
+  char *line = NULL; size_t lcap = 0;
+  if (pipe(fd) != 0) return -1;
+  pid = fork();
+  if (pid < 0) return -1;
+  if (pid == 0) {
+    struct genome_struct g1, g2;
+    close(fd[0]);
+    memset(&g1, 0, sizeof g1); memset(&g2, 0, sizeof g2);
+    g1.genes = (int *)src; g2.genes = (int *)dst;
+    outfile = fdopen(fd[1], "w");
+    print_scenario_2(&g1, &g2, n, 0, 4);
+    fflush(outfile);
+    _exit(0);
+  }
+  close(fd[1]);
+  in = fdopen(fd[0], "r");
+  while (nsteps < cap && getline(&line, &lcap, in) > 0) {
+    int k, s, sv, e, ev;
+    if (strncmp(line, "Step ", 5) == 0 &&
+        sscanf(line, "Step %d: Chrom. 0, gene %d [%d] through chrom. 0, gene %d [%d]",
+               &k, &s, &sv, &e, &ev) == 5) {
+      steps[2*nsteps] = s; steps[2*nsteps+1] = e; nsteps++;
+    }
+  }
+  kill(pid, SIGKILL);
+  fclose(in);
+  waitpid(pid, NULL, 0);
+  free(line);
+  return nsteps;
+}

@@ -32,7 +32,7 @@ extern "C" int emu_scenario(const int32_t *src, const int32_t *dst, int npairs, 
   grsr::pick_shape(n, threads, &t, &e);
   size_t smem = grsr::work_bytes(n, t * e, true) + grsr::scen_extra_bytes(n);
   GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
-    grsr::scenario_kernel<kNt, kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, 0);
+    grsr::scenario_kernel<kNt, kEpt>(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, grsr::PairQueue{&ticket, 0, 1}, 0);
   }));
   return 0;
 }
@@ -59,7 +59,7 @@ extern "C" int emu_scenario_large(const int32_t *src, const int32_t *dst, int np
   std::vector<unsigned char> scratch(grsr::scen_large_bytes(n) * (size_t)grid + 64);
   unsigned char *sc = scratch.data();
   emu::launch((unsigned)grid, (unsigned)threads, 0, [&] {
-    grsr::scenario_large_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, sc);
+    grsr::scenario_large_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, grsr::PairQueue{&ticket, 0, 1}, sc);
   });
   return 0;
 }
@@ -91,7 +91,7 @@ extern "C" int emu_scenario_cluster(const int32_t *src, const int32_t *dst, int 
   unsigned char *sc = scratch.data();
   unsigned long long *xp = xch.data();
   emu::launch_clusters((unsigned)nclusters, (unsigned)cs, (unsigned)threads, 34 * 8, [&] {
-    grsr::scenario_cluster_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, &ticket, sc, xp);
+    grsr::scenario_cluster_kernel(src, dst, npairs, n, steps, nsteps, max_steps, status, evals, grsr::PairQueue{&ticket, 0, 1}, sc, xp);
   });
   return 0;
 }
@@ -149,7 +149,7 @@ extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int
   int32_t *st2p = st2.data();
   GRSR_DISPATCH_SHAPE(t, e, emu::launch(2, (unsigned)t, smem, [&] {
     grsr::scenario_kernel<kNt, kEpt>(cs, dst, npairs, n, steps, nsteps, max_steps, st2p,
-                                     (unsigned long long *)nullptr, &ticket, 1);
+                                     (unsigned long long *)nullptr, grsr::PairQueue{&ticket, 0, 1}, 1);
   }));
   for (int p = 0; p < npairs; p++) if (status[p] == 0) status[p] = st2[p];
   return 0;
@@ -167,20 +167,20 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   emu::launch(2, 64, 0, [&] { grsr::signed_inverse_kernel(genomes, sp, total, n); });
   int shift = grsr::walk_shape_arg(grsr::walk_shift(n), grsr::kWalkIdle);
   std::vector<int32_t> dl((size_t)npairs + 1, -1);
-  unsigned dc = 0, flag = 0;
+  unsigned dc = 0, flag = 0, tk1 = 0, tk2 = 0;
   int32_t *dlp = dl.data();
-  unsigned *dcp = &dc, *fp = (shared < 0) ? &flag : nullptr;
+  unsigned *dcp = &dc, *fp = (shared < 0) ? &flag : nullptr, *t1 = &tk1, *t2 = &tk2;
   if (fp) emu::launch(3, 64, 0, [&] { grsr::walk_order_kernel(pairs, npairs, fp); });
   if (shared != 0) {
     size_t smem = 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * (size_t)wpb;
     emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
-      grsr::dist_walk_shared_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp);
+      grsr::dist_walk_shared_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp, t1);
     });
   }
   if (shared != 1) {
     size_t smem = grsr::walk_warp_bytes(n) * (size_t)wpb;
     emu::launch((unsigned)grid, (unsigned)(32 * wpb), smem, [&] {
-      grsr::dist_walk_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp);
+      grsr::dist_walk_kernel(genomes, sp, n, pairs, npairs, out, stride, shift, dlp, dcp, fp, t2);
     });
   }
   *deferred = (int)dc;
