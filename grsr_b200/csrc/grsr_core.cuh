@@ -23,6 +23,7 @@
 // the CPU test-suite to debug kernel logic); nothing in the product selects that build.
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 #ifndef GRSR_EMU
 #include <cooperative_groups.h>
 #endif
@@ -338,11 +339,75 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
   return x;
 }
 
+// Ordered compaction of RUN STARTS (TeamBlock only): among the i in [0,N) with f(i, value) true, taken
+// in increasing i, keeps value(i) whenever it differs from the value of the previous kept i -- the
+// run-length encoding of the filtered sequence in ONE counting and ONE writing sweep (instead of
+// compacting the sequence and then its run starts).  Each warp owns a contiguous chunk; a chunk's
+// first run merges into the previous non-empty chunk's last run when their values are equal.
+// values must be < 2^21 (packed per-warp records).  Returns the number of runs.
+template <class VT, class F>
+__device__ inline int blk_compact_runs(int N, F f, VT *out, unsigned long long *red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned kNoVal = 0x1FFFFFu;
+  const int chunk = (((N + nw - 1) / nw) + 31) & ~31;
+  const int lo = wid * chunk, hi = min(N, lo + chunk);
+  unsigned cnt = 0, first = kNoVal, carry = kNoVal;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane; unsigned val = 0;
+    const bool ok = (i < hi) && f(i, val);
+    const unsigned m = __ballot_sync(kFull, ok);
+    if (m == 0u) continue;
+    const unsigned below = m & lt;
+    const unsigned pv = __shfl_sync(kFull, val, below ? 31 - __clz((int)below) : 0);
+    const unsigned prev = below ? pv : carry;
+    cnt += __popc(__ballot_sync(kFull, ok && val != prev));
+    if (first == kNoVal) first = __shfl_sync(kFull, val, __ffs((int)m) - 1);
+    carry = __shfl_sync(kFull, val, 31 - __clz((int)m));
+  }
+  if (lane == 0) red[wid] = ((unsigned long long)cnt << 42) | ((unsigned long long)first << 21) | carry;
+  __syncthreads();
+  // every thread walks the <= 32 records: position of my chunk's first run and the value before it
+  unsigned pos = 0, total = 0, before = kNoVal, running = kNoVal;
+  for (int w = 0; w < nw; w++) {
+    const unsigned long long r = red[w];
+    unsigned c = (unsigned)(r >> 42);
+    const unsigned fv = (unsigned)(r >> 21) & kNoVal, lv = (unsigned)r & kNoVal;
+    if (w == wid) before = running;
+    if (fv != kNoVal) {
+      if (fv == running) c--;                       // first run continues the previous chunk's last run
+      running = lv;
+    }
+    if (w < wid) pos += c;
+    total += c;
+  }
+  carry = before;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane; unsigned val = 0;
+    const bool ok = (i < hi) && f(i, val);
+    const unsigned m = __ballot_sync(kFull, ok);
+    if (m == 0u) continue;
+    const unsigned below = m & lt;
+    const unsigned pv = __shfl_sync(kFull, val, below ? 31 - __clz((int)below) : 0);
+    const unsigned prev = below ? pv : carry;
+    const bool start = ok && val != prev;
+    const unsigned sm = __ballot_sync(kFull, start);
+    if (start) out[pos + __popc(sm & lt)] = (VT)val;
+    pos += __popc(sm);
+    carry = __shfl_sync(kFull, val, 31 - __clz((int)m));
+  }
+  __syncthreads();
+  return (int)total;
+}
+
 // --------------------------------------------------------------------------------------------------
 // Hurdles and fortress for a graph that has at least one unoriented cycle.
 // Entry state: A2[v] = cycle id (leftmost vertex) or NONE for adjacency vertices;
 //              A1[r] = 1 if cycle r (r = its leftmost vertex, always even) owns an oriented grey
-//              edge, else 0.  P is free (it may alias the jumping words, which are dead by now).
+//              edge, else 0;
+//              P[r] = r and P[r+1] = 0 for every cycle r (the union-find forest and the reach, "S1",
+//              written by the caller together with A2 / A1; P may alias the jumping words, which are
+//              dead by now).
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
 template <class TM, class VT>
@@ -354,47 +419,38 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   uint32_t *W = wk.P; VT *A1 = wk.A1, *A2 = wk.A2, *BLK = wk.BLK;
   VT *bmin = BLK, *bmax = BLK + wk.NB;
 
-  GRSR_PHASE(20);
-  // S1: start the union-find forest (W[r] = r) and the reach (W[r+1] = rightmost vertex of
-  //     cycle r, filled by S2).
-  for (int k = tid; k <= n; k += nt) {
-    unsigned a = 2u * k;
-    if (A2[a] == a) { W[a] = a; W[a + 1] = 0; }
-  }
-  TM::sync();
-
-  GRSR_PHASE(21);
   // S2: reach of every cycle = max vertex carrying its id (reference: right[], G/graph_edit.c:392).
-  //     Lanes hold consecutive vertices, so the highest lane of each equal-id group carries the max.
-  for (int base = tid & ~31; base < S; base += nt) {
-    int v = base + lane;
-    unsigned c = (v < S) ? A2[v] : kNone;
-    unsigned grp = __match_any_sync(kFull, c);
-    if (c != kNone && lane == 31 - __clz((int)grp)) atomicMax(&W[c + 1], (uint32_t)v);
+  //     Vertices are visited from the right, so the first sweep already holds the reach of every long
+  //     cycle and later vertices only compare; the atomic is issued by the few that still improve it.
+  GRSR_PHASE(21);
+  for (int v = S - 1 - tid; v >= 0; v -= nt) {
+    const unsigned c = A2[v];
+    if (c != kNone && W[c + 1] < (uint32_t)v) atomicMax(&W[c + 1], (uint32_t)v);
   }
   TM::sync();
 
+  // S3: per block of 32 vertices: smallest cycle id and largest reach seen in it (one warp per block).
   GRSR_PHASE(22);
-  // S3: per block of 32 vertices: smallest cycle id and largest reach seen in it.
-  for (int B = tid; B < wk.NB; B += nt) {
+  for (int B = tid >> 5; B < wk.NB; B += nt >> 5) {
+    const int v = (B << 5) + lane;
     unsigned mn = kNone, mx = 0;
-    for (int j = 0; j < 32; j++) {
-      int v = (B << 5) + ((j + B) & 31);       // rotated start: conflict-free across lanes
-      if (v < S) {
-        unsigned c = A2[v];
-        if (c != kNone) { mn = min(mn, c); mx = max(mx, W[c + 1]); }
-      }
+    if (v < S) {
+      const unsigned c = A2[v];
+      if (c != kNone) { mn = c; mx = W[c + 1]; }
     }
-    bmin[B] = (VT)mn; bmax[B] = (VT)mx;
+    mn = __reduce_min_sync(kFull, mn);
+    mx = __reduce_max_sync(kFull, mx);
+    if (lane == 0) { bmin[B] = (VT)mn; bmax[B] = (VT)mx; }
   }
   TM::sync();
 
-  GRSR_PHASE(23);
   // S4: for every cycle P = (l, r): among the vertices strictly inside (l, r), the smallest cycle id
   //     (a cycle that starts left of P and reaches into it) and the largest reach (a cycle that
   //     reaches into P and ends right of it).  Those two neighbours are enough to recover the
   //     components of the reference's stack sweep (G/graph_components.c:101-138).
-  //     A short extent is scanned by the cycle's own lane; long ones are handed to the whole warp.
+  //     A short extent is scanned by the cycle's own lane (four vertices per round, so that the
+  //     dependent id -> reach loads overlap); long ones are handed to the whole warp.
+  GRSR_PHASE(23);
   for (int base = tid & ~31; base <= n; base += nt) {
     int k = base + lane;
     unsigned r0 = 0, R0 = 0; bool isroot = false, big = false;
@@ -403,8 +459,16 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
       big = (R0 - r0) > 48u;
       if (!big) {
         unsigned mn = kNone, mx = 0;
-        for (unsigned v = r0 + 1; v < R0; v++) {
-          unsigned c = A2[v];
+        unsigned v = r0 + 2;                           // r0 + 1 is P's own vertex (black edge r0, r0+1)
+        for (; v + 4 <= R0; v += 4) {
+          const unsigned c0 = A2[v], c1 = A2[v + 1], c2 = A2[v + 2], c3 = A2[v + 3];
+          const unsigned x0 = (c0 != kNone) ? W[c0 + 1] : 0u, x1 = (c1 != kNone) ? W[c1 + 1] : 0u;
+          const unsigned x2 = (c2 != kNone) ? W[c2 + 1] : 0u, x3 = (c3 != kNone) ? W[c3 + 1] : 0u;
+          mn = min(mn, min(min(c0, c1), min(c2, c3)));
+          mx = max(mx, max(max(x0, x1), max(x2, x3)));
+        }
+        for (; v < R0; v++) {
+          const unsigned c = A2[v];
           if (c != kNone) { mn = min(mn, c); mx = max(mx, W[c + 1]); }
         }
         unsigned lk1 = (mn < r0) ? mn : kNoLink;
@@ -449,14 +513,16 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   }
   TM::sync();
 
-  GRSR_PHASE(24);
   // S5: connected components of the cycles under those links: hook larger root under smaller,
-  //     compress, repeat until no link joins two trees.
-  for (;;) {
+  //     compress, repeat until no link joins two trees.  The reach (W[r+1]) is not needed any more:
+  //     the first sweep clears it, S6 reuses the word as the component's orientation flag.
+  GRSR_PHASE(24);
+  for (bool first_sweep = true;; first_sweep = false) {
     int changed = 0;
     for (int k = tid; k <= n; k += nt) {
       unsigned r = 2u * k;
       if (A2[r] != r) continue;
+      if (first_sweep) W[r + 1] = 0;
       unsigned me = uf_find(W, r);
       unsigned l1 = A1[r] & kNoLink, l2 = A1[r + 1];
       if (l1 != kNoLink) {
@@ -477,43 +543,46 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     TM::sync();
   }
 
-  GRSR_PHASE(25);
   // S6: a component is oriented iff one of its cycles is (G/graph_components.c:309-336).
-  //     W[c+1] of the component root c becomes that flag (the reach is no longer needed).
-  for (int k = tid; k <= n; k += nt) {
-    unsigned r = 2u * k;
-    if (A2[r] == r) W[r + 1] = 0;
-  }
-  TM::sync();
+  //     W[c+1] of the component root c becomes that flag.
+  GRSR_PHASE(25);
   for (int k = tid; k <= n; k += nt) {
     unsigned r = 2u * k;
     if (A2[r] == r && (A1[r] & 1u)) W[W[r] + 1] = 1;
   }
   TM::sync();
 
+  // S7 + S8: the vertices of unoriented components, in vertex order, as component ids (the filtered
+  //     scan of G/graph_components.c:566-585); runs of equal ids = the reference's "blocks", one
+  //     entry per run.
   GRSR_PHASE(26);
-  // S7: the vertices of unoriented components, in vertex order, as a list of component ids
-  //     (the filtered scan of G/graph_components.c:566-585).
-  int m = TM::compact(S, [&](int v, unsigned &val) -> bool {
+  auto unoriented_comp = [&](int v, unsigned &val) -> bool {
     unsigned c = A2[v];
     if (c == kNone) return false;
     unsigned comp = W[c];
     if (W[comp + 1]) return false;
     val = comp; return true;
-  }, A1, wk);
-  if (m == 0) return 0;
+  };
+  int nb;
+  const VT *run;
+  if constexpr (std::is_same<TM, TeamBlock>::value) {
+    nb = blk_compact_runs(S, unoriented_comp, A1, wk.red);   // A1's flags and links are dead by now
+    run = A1;
+    if (nb == 0) return 0;
+  } else {
+    int m = TM::compact(S, unoriented_comp, A1, wk);
+    if (m == 0) return 0;
+    GRSR_PHASE(27);
+    nb = TM::compact(m, [&](int t, unsigned &val) -> bool {
+      unsigned c = A1[t];
+      if (t > 0 && A1[t - 1] == c) return false;
+      val = c; return true;
+    }, A2, wk);
+    run = A2;
+  }
 
-  GRSR_PHASE(27);
-  // S8: runs of equal ids = the reference's "blocks"; keep one entry per run.
-  int nb = TM::compact(m, [&](int t, unsigned &val) -> bool {
-    unsigned c = A1[t];
-    if (t > 0 && A1[t - 1] == c) return false;
-    val = c; return true;
-  }, A2, wk);
-  const VT *run = A2;
-
-  GRSR_PHASE(28);
   // S9: per component: number of runs (W[c]) and 1 + index of its last run (W[c+1]).
+  GRSR_PHASE(28);
   for (int t = tid; t < nb; t += nt) { unsigned c = run[t]; W[c] = 0; W[c + 1] = 0; }
   TM::sync();
   for (int t = tid; t < nb; t += nt) {
@@ -676,7 +745,8 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   // successors (in batches, loads before stores), merges and publishes.
   GRSR_PHASE_REL(1);
   {
-    constexpr int UB = (EPT < 8) ? EPT : 8;
+    constexpr int UB = (EPT < 8) ? EPT : (EPT % 8 == 0 ? 8 : (EPT % 6 == 0 ? 6 : 5));   // gathers per batch; divides EPT
+    static_assert(EPT % UB == 0, "words per thread must split into whole gather batches");
     uint32_t R[EPT];
 #pragma unroll
     for (int j = 0; j < EPT; j++) R[j] = W[tid + j * NT];
@@ -740,6 +810,9 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
       const unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(w0 >> 17, w1 >> 17);
       A2w[k] = cy | (cy << 16);
       wk.A1[a] = (uint16_t)((w0 >> 1) & 1u);
+      // S1 of the component analysis: forest and reach of a cycle live in the two words of its
+      // leftmost black edge (the jumping words of this edge have just been read by this thread)
+      if (cy == a) { W[a] = a; W[a + 1] = 0; }
     }
     __syncthreads();
     unsigned hf = hurdles_slow_path<TeamBlock>(wk, n);
@@ -850,6 +923,7 @@ __device__ inline Stats dist_core_large(WorkT<uint32_t> &wk, int n, EndsFn ends)
       const unsigned cy = (w0 & GRSR_W_ADJ) ? kNone : min(GRSR_L_LABEL(w0), GRSR_L_LABEL(w1));
       wk.A2[a] = cy; wk.A2[a + 1] = cy;
       wk.A1[a] = (unsigned)((w0 >> 1) & 1ull);
+      if (cy == a) { wk.P[a] = a; wk.P[a + 1] = 0; }
     }
     TM::sync();
     unsigned hf = hurdles_slow_path<TM>(wk, n);
@@ -932,6 +1006,7 @@ __host__ inline bool shape_exists(int t, int e) {
   if (t == 64) return e == 8 || e == 16;
   if (t == 128 || t == 256) return e == 8 || e == 16 || e == 32;
   if (t == 512) return e == 8 || e == 16 || e == 32 || e == 64;
+  if (t == 1024) return e == 10 || e == 12 || e == 16;
   return false;
 }
 
@@ -945,6 +1020,11 @@ __host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ep
     while (t < 512 && t * 16 < S) t *= 2;
     while (e < 64 && t * e < S) e *= 2;
   }
+  // 8192 < S <= 16384 (config 4: n = 5000): one pair's graph takes so much shared memory that at most
+  // one or two blocks fit per SM whatever their size, so the block is made as large as it can be
+  // (1024 threads: twice the warps to hide the shared-memory latency of every pass) with just enough
+  // words per thread (10 / 12 / 16: the jumping array is not padded to the next power of two)
+  if (S > 8192 && S <= 16384) { t = 1024; e = (S <= 10240) ? 10 : (S <= 12288 ? 12 : 16); }
   if (forced_threads > 0) {
     int fe = 1;
     while (fe < 64 && forced_threads * fe < S) fe *= 2;
@@ -966,11 +1046,13 @@ __host__ inline void pick_shape(int n, int forced_threads, int *threads, int *ep
     GRSR_SHAPE_CASE(128, 32, __VA_ARGS__) GRSR_SHAPE_CASE(256, 8, __VA_ARGS__)        \
     GRSR_SHAPE_CASE(256, 16, __VA_ARGS__) GRSR_SHAPE_CASE(256, 32, __VA_ARGS__)       \
     GRSR_SHAPE_CASE(512, 8, __VA_ARGS__) GRSR_SHAPE_CASE(512, 16, __VA_ARGS__)        \
-    GRSR_SHAPE_CASE(512, 32, __VA_ARGS__) GRSR_SHAPE_CASE(512, 64, __VA_ARGS__) {}    \
+    GRSR_SHAPE_CASE(512, 32, __VA_ARGS__) GRSR_SHAPE_CASE(512, 64, __VA_ARGS__)       \
+    GRSR_SHAPE_CASE(1024, 10, __VA_ARGS__) GRSR_SHAPE_CASE(1024, 12, __VA_ARGS__)     \
+    GRSR_SHAPE_CASE(1024, 16, __VA_ARGS__) {}                                         \
   } while (0)
 
 // registers per thread are capped so that the shared-memory-limited number of blocks fits
-#define GRSR_MIN_BLOCKS(NT, EPT) ((EPT) > 16 ? 1 : ((NT) >= 512 ? 3 : ((NT) == 256 ? 6 : ((NT) == 128 ? 10 : 16))))
+#define GRSR_MIN_BLOCKS(NT, EPT) ((EPT) > 16 || (NT) > 512 ? 1 : ((NT) >= 512 ? 3 : ((NT) == 256 ? 6 : ((NT) == 128 ? 10 : 16))))
 
 // Batched distance: pair p = (gamma row pairs[2p], pi row pairs[2p+1]) as in setinvmatrix
 // (reference G/uniinvdist.c:80-90).  stride 1: out[p] = d; stride 5: out[5p..] = {d,b,c,h,f}.

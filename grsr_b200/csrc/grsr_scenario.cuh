@@ -195,11 +195,49 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
       }, BPL, wk);
       const bool filter = (g0.h == 0);                        // G/opt_scenario.c:951
 
-      unsigned long long lastkey = kNoKey;
       int fi = -1, fj = -1;
-      // smallest reversal length found so far in the current search, shared by the block: a lane
-      // whose orbit partner is far away stops scanning as soon as somebody has a shorter candidate
-      for (;;) {
+      if (!filter) {
+        // Hurdles present: no filter, every pair of breakpoint edges (e1 < e2) is a candidate
+        // (i = e1, j = e2 - 1) and gets a full evaluation, in (j - i, i) order, until one yields
+        // d - 1 (G/opt_scenario.c:951, 527-576).  One diagonal j - i = g at a time: its candidates are
+        // listed in order (INV0 is free once G0 is built) and evaluated one after another; the next
+        // diagonal is the smallest gap > g that occurs between two breakpoint edges.
+        SV *CL = INV0;
+        for (int g = 0; fi < 0;) {
+          GRSR_PHASE(7);
+          unsigned long long mg = kNoKey;
+          for (int t = tid; t < nbp; t += nt) {
+            const int need = (int)BPL[t] + 1 + g;
+            int lo = t + 1, hi = nbp;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)BPL[mid] < need) lo = mid + 1; else hi = mid; }
+            if (lo < nbp) { const unsigned long long gg = (unsigned long long)((int)BPL[lo] - (int)BPL[t] - 1); mg = gg < mg ? gg : mg; }
+          }
+          mg = team_min64(TM(), mg, wk);
+          if (mg == kNoKey) break;                            // no candidate left at all
+          g = (int)mg;
+          const int nc = TM::compact(nbp, [&](int t, unsigned &val) -> bool {
+            const int want = (int)BPL[t] + 1 + g;
+            int lo = t + 1, hi = nbp;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)BPL[mid] < want) lo = mid + 1; else hi = mid; }
+            if (lo >= nbp || (int)BPL[lo] != want) return false;
+            val = (unsigned)BPL[t]; return true;
+          }, CL, wk);
+          for (int q = 0; q < nc; q++) {
+            const int i = (int)CL[q], j = i + g;
+            EndsTrial<SV> et; et.rho0 = RHO0; et.i = i; et.j = j;
+            GRSR_PHASE_BASE(8);
+            const Stats t1 = Pol::template dist<false>(wk, n, et);  // G/opt_scenario.c:974-986
+            nevals++;
+            if (t1.d == g0.d - 1) { fi = i; fj = j; break; }
+          }
+          g++;
+        }
+      }
+      unsigned long long lastkey = kNoKey;
+      // hurdle-free graph: the smallest reversal length found so far in the current search is shared
+      // by the block: a lane whose orbit partner is far away stops scanning as soon as somebody has a
+      // shorter candidate
+      while (filter) {
         // smallest key (j - i, i) greater than lastkey among admissible candidates
         GRSR_PHASE(7);
         if (tid == 0) *bound = 0xFFFFFFFFu;
@@ -216,15 +254,11 @@ __device__ inline void scenario_body(typename Pol::work &wk, typename Pol::sval 
             s = lo;
           }
           int e2 = -1;
-          if (filter) {
-            const unsigned want = ORB[2 * e1 + 1];
-            for (; s < nbp; s++) {
-              const int c = (int)BPL[s];
-              if ((unsigned)(c - e1 - 1) > *bound) break;     // cannot beat a candidate already found
-              if (ORB[2 * c] == want) { e2 = c; break; }
-            }
-          } else if (s < nbp) {
-            e2 = (int)BPL[s];
+          const unsigned want = ORB[2 * e1 + 1];
+          for (; s < nbp; s++) {
+            const int c = (int)BPL[s];
+            if ((unsigned)(c - e1 - 1) > *bound) break;       // cannot beat a candidate already found
+            if (ORB[2 * c] == want) { e2 = c; break; }
           }
           if (e2 >= 0) {
             const unsigned len0 = (unsigned)(e2 - e1 - 1);

@@ -35,7 +35,7 @@ CASES = {
     "rand12000": ("random", 12000, 12, 1500),
     "rand20000": ("random", 20000, 20, 1500),
 }
-CASES["hr5000_0"] = ("hurdle", 5000, 0, 6000)          # one WHOLE config-4 scenario (minutes of CPU)
+CASES["hr5000_0"] = ("hurdle", 5000, 0, 6000)          # one WHOLE config-4 scenario (3552 steps, an hour of one core)
 for s in range(1, 8):
     CASES["hr5000_%d" % s] = ("hurdle", 5000, s, 400)
 

@@ -189,3 +189,12 @@ def test_emulated_walk_shared_rows(n, wpb):
     sq = _ordered(len(g))
     got, _ = U.emu_stats_walk(g, sq, wpb, 2, shared=1)
     assert np.array_equal(got, U.orc_stats(g, sq))
+
+
+@pytest.mark.parametrize("n,count,seed", [(4200, 4, 11), (6000, 3, 12), (8000, 3, 13)])
+def test_emu_block_shapes_with_1024_threads(n, count, seed):
+    """8192 < 2n+2 <= 16384 (config 4's size range) runs 1024-thread blocks with 10 / 12 / 16 jumping
+    words per thread (pick_shape); hurdle-rich and random rows, every ordered pair, vs the oracle."""
+    g = U.mixed_genomes(n, count, seed=seed)
+    pairs = np.array([[i, j] for i in range(count) for j in range(count)], dtype=np.int32)
+    assert np.array_equal(U.emu_stats(g, pairs, threads=0, grid=2), U.orc_stats(g, pairs))
