@@ -58,12 +58,13 @@ def build_cuda(force: bool = False) -> str:
     return LIB
 
 
-def build_cuda_profile(force: bool = False) -> str:
-    """Diagnostic twin of the library with per-phase cycle counters compiled in (scripts/prof_phases.py)."""
-    out = os.path.join(LIBDIR, "libgrsr_cuda_prof.so")
+def build_cuda_profile(force: bool = False, tag: str = "", defines: tuple = ()) -> str:
+    """Diagnostic twin of the library with per-phase cycle counters compiled in (scripts/prof_phases.py);
+    tag / defines name experimental variants (e.g. tag="_x16", defines=("-DGRSR_SMALL_EXTENT=16",))."""
+    out = os.path.join(LIBDIR, "libgrsr_cuda_prof%s.so" % tag)
     os.makedirs(LIBDIR, exist_ok=True)
     if force or not _newer(out, cuda_sources()):
-        _run([_nvcc(), *NVCC_FLAGS, "-DGRSR_PHASE_PROFILE", "-o", out, os.path.join(CSRC, "grsr_capi.cu")])
+        _run([_nvcc(), *NVCC_FLAGS, "-DGRSR_PHASE_PROFILE", *defines, "-o", out, os.path.join(CSRC, "grsr_capi.cu")])
     return out
 
 
@@ -82,6 +83,18 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+DELE = os.path.join(BINDIR, "deleTransp")
+
+
+def build_dele_transp(force: bool = False) -> str:
+    """bin/deleTransp: host C restatement of scr/deleTransp.java (the step before grimm in reptA.sh)."""
+    os.makedirs(BINDIR, exist_ok=True)
+    src = os.path.join(CSRC, "dele_transp.c")
+    if force or not _newer(DELE, [src]):
+        _run(["gcc", "-O2", "-Wall", "-Wextra", "-std=gnu99", "-o", DELE, src])
+    return DELE
+
+
 def build_oracle() -> None:
     """Test infrastructure: the C restatement and, where /root/reference exists, the reference."""
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
@@ -95,6 +108,7 @@ def build_emu() -> None:
 def build_all(force: bool = False) -> None:
     build_cuda(force)
     build_cli(force)
+    build_dele_transp(force)
     build_oracle()
     build_emu()
 

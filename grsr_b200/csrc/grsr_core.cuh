@@ -342,20 +342,24 @@ __device__ inline unsigned uf_find(const uint32_t *W, unsigned x) {
 // Ordered compaction of RUN STARTS (TeamBlock only): among the i in [0,N) with f(i, value) true, taken
 // in increasing i, keeps value(i) whenever it differs from the value of the previous kept i -- the
 // run-length encoding of the filtered sequence in ONE counting and ONE writing sweep (instead of
-// compacting the sequence and then its run starts).  Each warp owns a contiguous chunk; a chunk's
-// first run merges into the previous non-empty chunk's last run when their values are equal.
-// values must be < 2^21 (packed per-warp records).  Returns the number of runs.
+// compacting the sequence and then its run starts).  The counting sweep leaves value(i) (or NONE) in
+// cache[i], so that the writing sweep does not evaluate f again; out may alias whatever f reads, but
+// not cache.  Each warp owns a contiguous chunk; a chunk's first run merges into the previous non-empty
+// chunk's last run when their values are equal (warp 0 sorts that out with shuffles).
+// values must be < 2^21 - 1 (packed per-warp records).  Returns the number of runs.
 template <class VT, class F>
-__device__ inline int blk_compact_runs(int N, F f, VT *out, unsigned long long *red) {
+__device__ inline int blk_compact_runs(int N, F f, VT *cache, VT *out, unsigned long long *red) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
   const unsigned kNoVal = 0x1FFFFFu;
+  constexpr unsigned kNone = none_of<VT>();
   const int chunk = (((N + nw - 1) / nw) + 31) & ~31;
   const int lo = wid * chunk, hi = min(N, lo + chunk);
   unsigned cnt = 0, first = kNoVal, carry = kNoVal;
   for (int base = lo; base < hi; base += 32) {
     const int i = base + lane; unsigned val = 0;
     const bool ok = (i < hi) && f(i, val);
+    if (i < hi) cache[i] = (VT)(ok ? val : kNone);
     const unsigned m = __ballot_sync(kFull, ok);
     if (m == 0u) continue;
     const unsigned below = m & lt;
@@ -367,24 +371,29 @@ __device__ inline int blk_compact_runs(int N, F f, VT *out, unsigned long long *
   }
   if (lane == 0) red[wid] = ((unsigned long long)cnt << 42) | ((unsigned long long)first << 21) | carry;
   __syncthreads();
-  // every thread walks the <= 32 records: position of my chunk's first run and the value before it
-  unsigned pos = 0, total = 0, before = kNoVal, running = kNoVal;
-  for (int w = 0; w < nw; w++) {
-    const unsigned long long r = red[w];
+  if (wid == 0) {
+    // lane w holds chunk w's record: start position of its runs and the value just before its chunk
+    const unsigned long long r = (lane < nw) ? red[lane] : ((unsigned long long)kNoVal << 21) | kNoVal;
     unsigned c = (unsigned)(r >> 42);
     const unsigned fv = (unsigned)(r >> 21) & kNoVal, lv = (unsigned)r & kNoVal;
-    if (w == wid) before = running;
-    if (fv != kNoVal) {
-      if (fv == running) c--;                       // first run continues the previous chunk's last run
-      running = lv;
-    }
-    if (w < wid) pos += c;
-    total += c;
+    const unsigned nonempty = __ballot_sync(kFull, fv != kNoVal);
+    const unsigned before_m = nonempty & lt;
+    const unsigned plv = __shfl_sync(kFull, lv, before_m ? 31 - __clz((int)before_m) : 0);
+    const unsigned before = before_m ? plv : kNoVal;
+    if (fv != kNoVal && fv == before) c--;              // first run continues the previous chunk's last run
+    unsigned incl = c;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += y; }
+    red[lane] = ((unsigned long long)(incl - c) << 32) | before;
+    if (lane == 31) red[32] = incl;
   }
-  carry = before;
+  __syncthreads();
+  unsigned pos = (unsigned)(red[wid] >> 32);
+  carry = (unsigned)red[wid];
+  const unsigned total = (unsigned)red[32];
   for (int base = lo; base < hi; base += 32) {
-    const int i = base + lane; unsigned val = 0;
-    const bool ok = (i < hi) && f(i, val);
+    const int i = base + lane;
+    const unsigned val = (i < hi) ? (unsigned)cache[i] : kNone;
+    const bool ok = val != kNone;
     const unsigned m = __ballot_sync(kFull, ok);
     if (m == 0u) continue;
     const unsigned below = m & lt;
@@ -410,6 +419,9 @@ __device__ inline int blk_compact_runs(int N, F f, VT *out, unsigned long long *
 //              dead by now).
 // Returns (h << 1) | f.
 // --------------------------------------------------------------------------------------------------
+#ifndef GRSR_SMALL_EXTENT
+#define GRSR_SMALL_EXTENT 48   // S4: extents up to this many vertices are scanned by one lane
+#endif
 template <class TM, class VT>
 __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   const int tid = TM::tid(), nt = TM::size(), lane = tid & 31;
@@ -456,7 +468,7 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     unsigned r0 = 0, R0 = 0; bool isroot = false, big = false;
     if (k <= n) { r0 = 2u * k; isroot = (A2[r0] == r0); if (isroot) R0 = W[r0 + 1]; }
     if (isroot) {
-      big = (R0 - r0) > 48u;
+      big = (R0 - r0) > (unsigned)GRSR_SMALL_EXTENT;
       if (!big) {
         unsigned mn = kNone, mx = 0;
         unsigned v = r0 + 2;                           // r0 + 1 is P's own vertex (black edge r0, r0+1)
@@ -566,8 +578,9 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   int nb;
   const VT *run;
   if constexpr (std::is_same<TM, TeamBlock>::value) {
-    nb = blk_compact_runs(S, unoriented_comp, A1, wk.red);   // A1's flags and links are dead by now
-    run = A1;
+    // A1's flags and links are dead by now: it caches the sweep's values; the runs replace the cycle ids
+    nb = blk_compact_runs(S, unoriented_comp, A1, A2, wk.red);
+    run = A2;
     if (nb == 0) return 0;
   } else {
     int m = TM::compact(S, unoriented_comp, A1, wk);

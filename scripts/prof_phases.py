@@ -8,7 +8,7 @@ Build the twin library first (here, it travels with the snapshot): python -c "fr
 import ctypes, os, sys, time, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["GRSR_LIB"] = os.path.join(ROOT, "grsr_b200", "lib", "libgrsr_cuda_prof.so")
+os.environ["GRSR_LIB"] = os.path.join(ROOT, "grsr_b200", "lib", "libgrsr_cuda_prof%s.so" % os.environ.get("GRSR_PROF_TAG", ""))
 import numpy as np
 from grsr_b200 import capi, gen
 
