@@ -55,7 +55,7 @@ G_CFG, N_CFG, SEED_CFG = 1000, 2000, 7
 METRIC = "reversal_distance_pairs_per_sec"
 UNIT = "pairs/s"
 BYTES_PER_PAIR = 8 * N_CFG + 4          # read pi and gamma as int32, write one int32 distance
-CONFIG4_PAIRS, CONFIG4_GENES, CONFIG4_STEP_CAP = 10000, 5000, 8
+CONFIG4_PAIRS, CONFIG4_GENES, CONFIG4_STEP_CAP = 10000, 5000, 16
 CONFIG5_GENES, CONFIG5_SEED, CONFIG5_PREFIX = 100000, 5, 2000
 I32P = ctypes.POINTER(ctypes.c_int)
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgrimmref.so")

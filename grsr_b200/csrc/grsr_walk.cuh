@@ -48,7 +48,7 @@ namespace grsr {
 
 static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a walk (or an adjacency end)
 static const int kWalkMaxNodes = 256;        // nodes (possible walk starts) per pair
-static const int kWalkMaxWalks = 256;        // walks per pair (8 words per lane in the jumping phase)
+static const int kWalkMaxWalks = 128;        // walks per pair (4 words per lane in the jumping phase; ids fit a byte)
 static const int kWalkGroup = 8;             // tau steps between two votes
 static const int kWalkIdle = 8;              // default: lanes that must be out of work before new walks start
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
@@ -65,30 +65,31 @@ __host__ __device__ inline int walk_shift(int n) {
 // kernel argument: node stride and start threshold in one int
 __host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return shift | (idle_min << 8); }
 
-// 32-bit words of H: n+2 used, padded so that 32 lanes x 16-byte loads cover it in whole rounds
-__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 127) & ~127; }
+// 32-bit words of H: n+2 used (entries 0 .. 2n+2), padded so that 32 lanes x 16-byte loads cover it in
+// whole rounds and at least 32 words (64 entries) stay free behind the used part: the list of
+// unclaimed vertices of the leftover phase lives there.
+__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 32 + 127) & ~127; }
+// entries of H (16-bit) that hold the leftover list: [2n+3, 2 * hwords), taken from the word boundary
+__host__ __device__ inline int walk_list_first(int n) { return (2 * n + 3 + 1) & ~1; }
+__host__ __device__ inline int walk_list_cap(int n) { return 2 * walk_hwords(n) - walk_list_first(n); }
 
-// shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[256] | MAP u16[256] | misc
+// shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[128] | MAP u8[256] | misc
 __host__ __device__ inline size_t walk_tail_bytes(int n) { return (((size_t)(n + 1) * 2) + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t walk_warp_bytes(int n) {
-  size_t b = walk_tail_bytes(n);
-  b += (size_t)walk_hwords(n) * 4;
-  b += (size_t)kWalkMaxWalks * 4;
-  b += (size_t)kWalkMaxNodes * 2;
-  b += 128;                                    // unoriented-cycle list: count + kWalkMaxUnoriented ids
-  return b;
+__host__ __device__ inline size_t walk_private_bytes(int n) {
+  return (size_t)walk_hwords(n) * 4 + (size_t)kWalkMaxWalks * 4 + (size_t)kWalkMaxNodes + 128;
 }
+__host__ __device__ inline size_t walk_warp_bytes(int n) { return walk_tail_bytes(n) + walk_private_bytes(n); }
 
 // The cycle a vertex lies on (leftmost vertex, i.e. orbit label with bit 0 cleared) and whether that
 // cycle owns an oriented grey edge: walk to the next start of a walk and read its converged word,
 // or get round an orbit that has none.
-__device__ inline unsigned walk_cycle_of(const uint16_t *H, const uint32_t *NW, const uint16_t *MAP,
+__device__ inline unsigned walk_cycle_of(const uint16_t *H, const uint32_t *NW, const uint8_t *MAP,
                                          unsigned v, unsigned mask, int shift, unsigned &oriented) {
   unsigned x = v, mn = v, orr = 0;
   for (;;) {
     if ((x & mask) == 0u) {
       const unsigned id = MAP[x >> shift];
-      if (id != 0xFFFFu) {
+      if (id != 0xFFu) {
         const uint32_t w = NW[id];
         oriented = ((orr & 1u) | ((w >> 1) & 1u));
         return (w >> 17) & ~1u;
@@ -185,18 +186,14 @@ struct WalkMem {
   const uint16_t *tail;     // [n+1] staged pi row (vertex where gene +a begins) + the sentinel entry
   uint32_t *Hw;             // successor table, 32-bit view ([walk_hwords])
   uint32_t *NW;             // [kWalkMaxWalks] walk words
-  uint16_t *MAP;            // [kWalkMaxNodes] node -> walk id
+  uint8_t *MAP;             // [kWalkMaxNodes] node -> walk id (0xFF: no walk started there)
   uint32_t *UL;             // [32] unoriented-cycle list and counters
 };
-
-__host__ __device__ inline size_t walk_private_bytes(int n) {
-  return (size_t)walk_hwords(n) * 4 + (size_t)kWalkMaxWalks * 4 + (size_t)kWalkMaxNodes * 2 + 128;
-}
 
 __device__ inline void walk_carve_private(WalkMem &wm, unsigned char *base, int n) {
   wm.Hw = (uint32_t *)base;   base += (size_t)walk_hwords(n) * 4;
   wm.NW = (uint32_t *)base;   base += (size_t)kWalkMaxWalks * 4;
-  wm.MAP = (uint16_t *)base;  base += (size_t)kWalkMaxNodes * 2;
+  wm.MAP = (uint8_t *)base;   base += (size_t)kWalkMaxNodes;
   wm.UL = (uint32_t *)base;
 }
 
@@ -219,7 +216,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   const int hwords = walk_hwords(n);
   const uint16_t *tail = wm.tail;
   uint32_t *Hw = wm.Hw, *NW = wm.NW, *UL = wm.UL;
-  uint16_t *MAP = wm.MAP;
+  uint8_t *MAP = wm.MAP;
   uint16_t *H = (uint16_t *)Hw;
   const unsigned mask = (1u << shift) - 1u;
   const int K = (S + (int)mask) >> shift;            // nodes 0 .. K-1 <-> vertices i << shift
@@ -228,7 +225,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   if (lane == 0) UL[0] = 0;
   {
     uint32_t *M32 = (uint32_t *)MAP;                  // no walk starts anywhere yet
-    for (int j = lane; j < (K + 1) / 2; j += 32) M32[j] = 0xFFFFFFFFu;
+    for (int j = lane; j < (K + 3) / 4; j += 32) M32[j] = 0xFFFFFFFFu;
   }
   __syncwarp();
 
@@ -326,7 +323,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
             myid = W + myrank;
             x = (unsigned)mynode << shift;
             H[x + 1] = (uint16_t)(e | kVis);
-            MAP[mynode] = (uint16_t)myid;
+            MAP[mynode] = (uint8_t)myid;
             nx = e; mn = x; orr = 0; ended = false;
           }
           const int last = (int)(SCR[take - 1] >> 16);  // lane of the last free node handed out
@@ -361,15 +358,15 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
 
   // ---- jumping over the walk words -----------------------------------------------------------------
   unsigned ncyc = 0, nun = 0;
-  if (W <= 128) walk_jump<4>(NW, UL, W, lane, ncyc, nun);
-  else walk_jump<8>(NW, UL, W, lane, ncyc, nun);
+  walk_jump<4>(NW, UL, W, lane, ncyc, nun);
 
   // ---- orbits without a node: list the unclaimed vertices, then one lane per vertex ---------------
-  // The list lives in the upper half of the walk words (free when at most 128 walks were started).
+  // The list lives in the free entries behind the used part of H; its entries carry bit 15, so the scan
+  // that fills it (whole rows of H, padding included) takes them for claimed entries.
   int defer = 0;
   {
-    uint16_t *LL = (uint16_t *)(NW + 128);
-    const unsigned llcap = (W <= 128) ? 256u : 0u;
+    uint16_t *LL = H + walk_list_first(n);
+    const unsigned llcap = (unsigned)walk_list_cap(n);
     if (lane == 0) UL[31] = 0;
     __syncwarp();
     const uint4 *H4 = (const uint4 *)Hw;
@@ -388,7 +385,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
             const int k = __ffs((int)um) - 1;
             um &= um - 1u;
             const unsigned pos = atomicAdd(&UL[31], 1u);
-            if (pos < llcap) LL[pos] = (uint16_t)((unsigned)(8 * q + k) - 1u);     // vertex of entry 8q+k
+            if (pos < llcap) LL[pos] = (uint16_t)((((unsigned)(8 * q + k) - 1u)) | kVis);  // vertex of entry 8q+k
           }
         }
       }
@@ -399,7 +396,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     else {
       int budget = kWalkLeftoverBudget;
       for (unsigned i = lane; i < cnt; i += 32) {
-        const unsigned u0 = LL[i];
+        const unsigned u0 = LL[i] & 0x7FFFu;
         unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
         bool root = true;
         while (x1 != u0) {
