@@ -534,11 +534,11 @@ def cli_leg():
         for k, row in enumerate(g2):
             f.write(">g%d\n%s $\n" % (k + 1, " ".join(str(int(x)) for x in row)))
 
-    def wall(binary, argv, reps):
+    def wall(binary, argv, reps, env=None):
         best, out = None, None
         for _ in range(reps):
             t0 = time.perf_counter()
-            r = subprocess.run([binary] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            r = subprocess.run([binary] + argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
             dt = time.perf_counter() - t0
             if r.returncode != 0:
                 return None, r.stderr.decode()[-200:]
@@ -550,11 +550,25 @@ def cli_leg():
         return "\n".join(ln for ln in text.splitlines() if not ln.startswith(("Running:", "Input:")))
 
     out = {}
+    # resident mode: one `grimm --server` keeps the CUDA context, the invocations hand themselves to it
+    sock = os.path.join(tmp, "bench_grsr.sock")
+    if os.path.exists(sock):
+        os.unlink(sock)
+    srv = subprocess.Popen([ours, "--server", sock], stderr=subprocess.DEVNULL)
+    for _ in range(600):
+        if os.path.exists(sock) or srv.poll() is not None:
+            break
+        time.sleep(0.05)
+    srv_env = dict(os.environ, GRSR_SERVER=sock) if os.path.exists(sock) else None
     for name, argv in (("config1_scenario_pair_1_2", ["-f", ex, "-C", "-g", "1,2"]),
                        ("config1_matrix", ["-f", ex, "-C", "-m"]),
                        ("config2_matrix_25x500", ["-f", cfg2, "-C", "-m"])):
         t_ours, o_ours = wall(ours, argv, 5)
         leg = {"argv": " ".join(argv[2:]), "grsr_wall_s": t_ours}
+        if srv_env:
+            t_res, o_res = wall(ours, argv, 20, env=srv_env)
+            leg["grsr_resident_wall_s"] = t_res
+            leg["resident_same_output"] = (o_res == o_ours)
         if os.path.exists(REF_BIN):
             t_ref, o_ref = wall(REF_BIN, argv, 5)
             leg["reference_wall_s"] = t_ref
@@ -567,6 +581,11 @@ def cli_leg():
         f.write(">a\n1 2 3 $\n>b\n1 -2 3 $\n")
     t_ours, _ = wall(ours, ["-f", tiny, "-L", "-d", "-g", "1,2"], 5)
     out["process_startup_s"] = t_ours
+    srv.kill()
+    srv.wait()
+    out["note"] = ("grsr_wall_s = one process per invocation (CUDA initialisation and context creation dominate); "
+                   "grsr_resident_wall_s = the same command line with GRSR_SERVER pointing at one `grimm --server` "
+                   "process; best of the repetitions")
     return out
 
 

@@ -46,7 +46,8 @@ def _run(cmd: list[str], cwd: str | None = None) -> None:
 
 
 def cuda_sources() -> list[str]:
-    return [os.path.join(CSRC, f) for f in ("grsr_capi.cu", "grsr_core.cuh", "grsr_scenario.cuh", "grsr_stepwise.cuh", "grsr_walk.cuh")] + [
+    return [os.path.join(CSRC, f) for f in ("grsr_capi.cu", "grsr_core.cuh", "grsr_scenario.cuh", "grsr_stepwise.cuh", "grsr_walk.cuh",
+                                               "grsr_unsigned.cuh", "grsr_unsigned_host.hpp")] + [
         os.path.join(ROOT, "include", "grsr.h")]
 
 

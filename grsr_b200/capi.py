@@ -44,6 +44,7 @@ SIGNATURES = {
                                            ctypes.c_int, ctypes.c_int]),
     "grsr_scenario_prefix": (ctypes.c_int, [I32P, I32P, ctypes.c_int, ctypes.c_int, I32P, I32P, ctypes.c_int,
                                             I32P, ctypes.POINTER(ctypes.c_int64), ctypes.c_int, ctypes.c_int]),
+    "grsr_unsigned_dist": (ctypes.c_int, [I32P, I32P, ctypes.c_int, ctypes.c_int, I32P, I32P, ctypes.c_void_p, ctypes.c_int]),
     "grsr_trial_distances": (ctypes.c_int, [I32P, I32P, ctypes.c_int, I32P, ctypes.c_int64, I32P, ctypes.c_int]),
     "grsr_signed_inverse_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                                ctypes.c_void_p]),
@@ -181,6 +182,23 @@ def scenario_prefix(src, dst, max_steps: int, first_device: int = 0, ngpus: int 
     _check(lib().grsr_scenario_prefix(_p(s), _p(d), npairs, n, _p(steps), _p(ns), max_steps, _p(done),
                                       ev.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), first_device, ngpus))
     return [steps[p, :ns[p]].copy() for p in range(npairs)], done.astype(bool), ev
+
+
+class UnsignedInfo(ctypes.Structure):
+    _fields_ = [("dist", ctypes.c_int32), ("approx", ctypes.c_int32), ("passes", ctypes.c_int32),
+                ("num_sing", ctypes.c_int32 * 2), ("num_doub", ctypes.c_int32 * 2)]
+
+
+def unsigned_dist(g1, g2, circular: bool = False, device: int = 0):
+    """(distance, optimally signed g1, optimally signed g2, info) of two unsigned genomes (grimm -u)."""
+    a = _i32(g1)
+    b = _i32(g2)
+    o1 = np.zeros_like(a)
+    o2 = np.zeros_like(b)
+    info = UnsignedInfo()
+    _check(lib().grsr_unsigned_dist(_p(a), _p(b), len(a), 1 if circular else 0, _p(o1), _p(o2),
+                                    ctypes.byref(info), device))
+    return info.dist, o1, o2, info
 
 
 def trial_distances(src, dst, cands, device: int = 0) -> np.ndarray:

@@ -1,7 +1,7 @@
 /* grimm_main.c -- host program with GRIMM 2.01's command line for the unichromosomal path
  * (reference G/mcmain.c:195-996), calling the B200 kernels through the C ABI of include/grsr.h.
  *
- *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 1..7] [-t 1] [-v]
+ *   grimm -f datafile [-o outfile] -L|-C [-g i,j] [-m] [-d] [-s] [-S 1..7] [-t 1] [-u] [-v]
  *
  * What is kept byte for byte (GRSR's scr/reptA.sh:61-62,453-454 greps this text):
  *   input format          mcread_data, check_genes, delete_caps   G/mcread_input.c:83-554
@@ -13,20 +13,45 @@
  *                         G/mcmain.c:1009-1283
  *   error texts + exit(-1)
  * What is NOT here: every number in the report comes from libgrsr_cuda.so (grsr_dist_pairs,
- * grsr_dist_matrix, grsr_stats_matrix, grsr_scenario_batch, grsr_trial_distances); this file holds
+ * grsr_dist_matrix, grsr_stats_matrix, grsr_scenario_batch, grsr_trial_distances, grsr_unsigned_dist
+ * for -u: unsigned_mcdist_nomem G/mcmain.c:808-815, set_unsigneddist_matrix :1155-1164); this file holds
  * no distance or scenario arithmetic.  -t 1 (print_rev_stats_t1, G/testrev.c:86-230) scores every
  * breakpoint-to-breakpoint reversal in one batched call.  Options outside the accelerated path
- * (multichromosomal mode, -c -z -t 2..4 -u -U -W -T -F -X -D -M) are refused with a message
+ * (multichromosomal mode, -c -z -t 2..4 -U -W -T -F -X -D -M) are refused with a message
  * instead of being silently mis-served.
+ *
+ * Resident mode (not in the reference; it exists because of how GRSR calls the program): scr/reptA.sh:61
+ * starts one `grimm` per genome pair on ~30-block genomes, and creating a CUDA context costs a process
+ * 0.4-1 s on a B200 box (profiles/r2_startup.txt) against 0.7 ms for the whole reference run.
+ *     grimm --server /path/to/socket &        one process that keeps the context (and the kernels) warm
+ *     GRSR_SERVER=/path/to/socket grimm ...   every other invocation: sends its argv, working directory,
+ *                                             stdout and stderr to that process and returns its exit status
+ * Without GRSR_SERVER, or when nobody listens there, the invocation runs in its own process as usual.
  */
 #include <ctype.h>
+#include <errno.h>
+#include <setjmp.h>
+#include <signal.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/un.h>
 #include <unistd.h>
 
 #include "grsr.h"
+
+/* In resident mode a request must not end the process: every exit() of the report code below lands in
+ * grimm_exit, which returns to the server loop instead. */
+static jmp_buf server_jmp;
+static int serving = 0;
+static void grimm_exit(int status)
+{
+  if (serving) longjmp(server_jmp, (status & 255) + 1);
+  exit(status);
+}
+#define exit(status) grimm_exit(status)
 
 #define MAX_STR_LEN 1024 /* G/mcstructs.h:47 */
 #define GNAME_WIDTH 20   /* G/mcmain.c:1008 */
@@ -482,13 +507,13 @@ static void legacy_scenario(FILE *out, const int32_t *g1, const int32_t *g2, int
   free(cur); free(succ); free(cands); free(d2);
 }
 
-int main(int argc, char *argv[])
+static int grimm_main(int argc, char *argv[])
 {
   int c, errflg = 0, i;
   const char *inputfname = NULL, *outputfname = NULL;
   struct stat statbuf;
   FILE *input;
-  int unichromosome = 0, circular = 0, verbose = 0;
+  int unichromosome = 0, circular = 0, verbose = 0, unsigned_dist = 0;
   int fn_distance = 0, fn_scenario = 0, scenario_type = 4, fn_any = 0, fn_matrix = 0, fn_revstats = 0;
   int gindex1 = -1, gindex2 = -1;
   char refused = 0;
@@ -527,7 +552,8 @@ int main(int argc, char *argv[])
       }
       fn_any = 1;
       break;
-    case 'c': case 'z': case 'u': case 'M': case 'D': case 'T': case 'X': case 'F':
+    case 'u': unsigned_dist = 1; break;
+    case 'c': case 'z': case 'M': case 'D': case 'T': case 'X': case 'F':
     case 'U': case 'W':
       refused = (char)c;
       break;
@@ -542,7 +568,7 @@ int main(int argc, char *argv[])
   if (errflg) die_usage(argv[0]);
   if (refused) {
     fprintf(stderr, "ERROR: option -%c is outside the path this build accelerates "
-                    "(unichromosomal -L/-C with -g -m -d -s -S -v); use the original GRIMM for it\n", refused);
+                    "(unichromosomal -L/-C with -g -m -d -s -S -t 1 -u -v); use the original GRIMM for it\n", refused);
     die_usage(argv[0]);
   }
 
@@ -624,14 +650,38 @@ int main(int argc, char *argv[])
   fprintf(outfile, "Running:                      \t%s\n", argv[0]);
   fprintf(outfile, "Input:                        \t%s\n", inputfname);
   fprintf(outfile, "Genome:                       \t%s\n", circular ? "Circular" : "Linear");
-  fprintf(outfile, "Signs:                        \t%s\n", "Signed");
+  fprintf(outfile, "Signs:                        \t%s\n", unsigned_dist ? "Unsigned" : "Signed");
   fprintf(outfile, "Number of Genomes:            \t%d\n", G);
   fprintf(outfile, "Number of Genes:              \t%d\n", n);
   fprintf(outfile, "Number of Chromosomes:        \t%d", 0);
   fprintf(outfile, " (unichromosomal)\n");
   fflush(outfile);
 
-  if (fn_matrix) {
+  if (fn_matrix && unsigned_dist) {
+    /* do_fn_distmatrix with set_unsigneddist_matrix (G/mcmain.c:1155-1164, G/unsigned.c:1107-1131): every
+     * pair through the unsigned distance; -v is ignored here as in the reference (:1133) */
+    int32_t *dm = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)G * (size_t)G, "distmatrix");
+    int j, dist_error = 0;
+    fprintf(outfile, "\nDistance Matrix:\n");
+    for (i = 0; i < G; i++) {
+      dm[(size_t)i * G + i] = 0;
+      for (j = i + 1; j < G; j++) {
+        grsr_unsigned_info_t info;
+        int rc = grsr_unsigned_dist(in.genes + (size_t)i * n, in.genes + (size_t)j * n, n, circular, NULL, NULL,
+                                    &info, first_device());
+        if (rc) gpu_fail(rc);
+        dm[(size_t)i * G + j] = dm[(size_t)j * G + i] = info.dist;
+        if (info.approx) dist_error = 1;
+      }
+    }
+    if (dist_error) {
+      fprintf(outfile, "WARNING: These unsigned permutations are too complex;\n");
+      fprintf(outfile, "some answers are approximated.\n");
+    }
+    fprintf(outfile, "\n   %d\n", G);
+    print_matrix_body(dm, 1, G, in.names, entry_width(dm, 1, G));
+    free(dm);
+  } else if (fn_matrix) {
     int rc;
     if (verbose) { /* do_fn_distmatrix_v, G/mcmain.c:1206-1283 */
       static const char *titles[5] = {"Distance", "Number of Breakpoints", "Number of Cycles",
@@ -671,10 +721,32 @@ int main(int argc, char *argv[])
       die_usage(argv[0]);
     }
     pair[0] = gindex1; pair[1] = gindex2;
-    rc = grsr_dist_pairs(in.genes, G, n, pair, 1, (int32_t *)&st, 5, first_device(), 1);
-    if (rc) gpu_fail(rc);
+    if (unsigned_dist) {
+      /* unsigned_mcdist_nomem (G/mcmain.c:808-815): the two genomes are overwritten with their optimal
+       * signs (circular: also shifts), everything after this works on the signed genomes */
+      grsr_unsigned_info_t info;
+      int32_t *s1 = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)n, "signed genome");
+      int32_t *s2 = (int32_t *)xmalloc(sizeof(int32_t) * (size_t)n, "signed genome");
+      int q;
+      rc = grsr_unsigned_dist(g1, g2, n, circular, s1, s2, &info, first_device());
+      if (rc) gpu_fail(rc);
+      if (circular) memcpy(in.genes + (size_t)gindex1 * (size_t)n, s1, sizeof(int32_t) * (size_t)n);
+      memcpy(in.genes + (size_t)gindex2 * (size_t)n, s2, sizeof(int32_t) * (size_t)n);
+      free(s1); free(s2);
+      if (verbose)
+        for (q = 0; q < info.passes; q++) {           /* assign_canon_signs, once per pass (G/unsigned.c:377-381) */
+          fprintf(outfile, "Number of Singletons:         \t%d\n", info.num_sing[q]);
+          fprintf(outfile, "Number of 2-strips:           \t%d\n", info.num_doub[q]);
+        }
+      if (info.approx)
+        fprintf(outfile, "WARNING: These unsigned permutations are too complex; answers are approximated.\n");
+      st.d = info.dist; st.b = st.c = st.h = st.f = 0;
+    } else {
+      rc = grsr_dist_pairs(in.genes, G, n, pair, 1, (int32_t *)&st, 5, first_device(), 1);
+      if (rc) gpu_fail(rc);
+    }
 
-    if (verbose) {
+    if (verbose && !unsigned_dist) {
       fprintf(outfile, "Number of Breakpoints:         \t%d\n", st.b);
       fprintf(outfile, "Number of Cycles:              \t%d\n", st.c);
       fprintf(outfile, "Number of Hurdles:             \t%d\n", st.h);
@@ -783,4 +855,152 @@ int main(int argc, char *argv[])
   free(in.genes);
   if (outfile != stdout) fclose(outfile);
   return 0;
+}
+
+#undef exit
+
+/* ---- resident mode ------------------------------------------------------------------------------------- */
+
+static int send_all(int fd, const void *buf, size_t len)
+{
+  const char *p = (const char *)buf;
+  while (len) { ssize_t k = write(fd, p, len); if (k <= 0) { if (errno == EINTR) continue; return -1; } p += k; len -= (size_t)k; }
+  return 0;
+}
+static int recv_all(int fd, void *buf, size_t len)
+{
+  char *p = (char *)buf;
+  while (len) { ssize_t k = read(fd, p, len); if (k <= 0) { if (k < 0 && errno == EINTR) continue; return -1; } p += k; len -= (size_t)k; }
+  return 0;
+}
+
+/* client: hand this invocation to the resident process; -1 = nobody there (run locally) */
+static int run_remote(const char *path, int argc, char **argv)
+{
+  struct sockaddr_un addr;
+  struct msghdr msg;
+  struct iovec iov;
+  char cbuf[CMSG_SPACE(2 * sizeof(int))], cwd[4096];
+  struct cmsghdr *cm;
+  int fd, i, hdr[2], fds[2] = {1, 2}, status = 255;
+  if (strlen(path) >= sizeof addr.sun_path) return -1;
+  fd = socket(AF_UNIX, SOCK_STREAM, 0);
+  if (fd < 0) return -1;
+  memset(&addr, 0, sizeof addr);
+  addr.sun_family = AF_UNIX;
+  strcpy(addr.sun_path, path);
+  if (connect(fd, (struct sockaddr *)&addr, sizeof addr) != 0) { close(fd); return -1; }
+  if (!getcwd(cwd, sizeof cwd)) strcpy(cwd, "/");
+  fflush(stdout); fflush(stderr);
+  hdr[0] = argc; hdr[1] = (int)strlen(cwd);
+  memset(&msg, 0, sizeof msg);
+  iov.iov_base = hdr; iov.iov_len = sizeof hdr;
+  msg.msg_iov = &iov; msg.msg_iovlen = 1;
+  msg.msg_control = cbuf; msg.msg_controllen = sizeof cbuf;
+  cm = CMSG_FIRSTHDR(&msg);
+  cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(2 * sizeof(int));
+  memcpy(CMSG_DATA(cm), fds, sizeof fds);                       /* our stdout and stderr travel with the request */
+  if (sendmsg(fd, &msg, 0) != (ssize_t)sizeof hdr) { close(fd); return -1; }
+  if (send_all(fd, cwd, (size_t)hdr[1])) { close(fd); return -1; }
+  for (i = 0; i < argc; i++) {
+    int len = (int)strlen(argv[i]);
+    if (send_all(fd, &len, sizeof len) || send_all(fd, argv[i], (size_t)len)) { close(fd); return -1; }
+  }
+  if (recv_all(fd, &status, sizeof status)) status = 255;
+  close(fd);
+  return status;
+}
+
+/* one request on connection fd: receive argv / cwd / the client's stdout and stderr, run the report
+ * with them, send the exit status back */
+static void serve_one(int fd)
+{
+  struct msghdr msg;
+  struct iovec iov;
+  char cbuf[CMSG_SPACE(2 * sizeof(int))], *cwd = NULL, **argv = NULL;
+  struct cmsghdr *cm;
+  int hdr[2], fds[2] = {-1, -1}, i, status = 255, argc = 0, save1, save2, jr;
+  memset(&msg, 0, sizeof msg);
+  iov.iov_base = hdr; iov.iov_len = sizeof hdr;
+  msg.msg_iov = &iov; msg.msg_iovlen = 1;
+  msg.msg_control = cbuf; msg.msg_controllen = sizeof cbuf;
+  if (recvmsg(fd, &msg, 0) != (ssize_t)sizeof hdr) return;
+  cm = CMSG_FIRSTHDR(&msg);
+  if (cm && cm->cmsg_level == SOL_SOCKET && cm->cmsg_type == SCM_RIGHTS && cm->cmsg_len == CMSG_LEN(2 * sizeof(int)))
+    memcpy(fds, CMSG_DATA(cm), sizeof fds);
+  if (fds[0] < 0 || hdr[0] < 1 || hdr[0] > 4096 || hdr[1] < 0 || hdr[1] > 65536) goto done;
+  argc = hdr[0];
+  cwd = (char *)calloc((size_t)hdr[1] + 1, 1);
+  argv = (char **)calloc((size_t)argc + 1, sizeof(char *));
+  if (!cwd || !argv || recv_all(fd, cwd, (size_t)hdr[1])) goto done;
+  for (i = 0; i < argc; i++) {
+    int len;
+    if (recv_all(fd, &len, sizeof len) || len < 0 || len > 1 << 20) goto done;
+    argv[i] = (char *)calloc((size_t)len + 1, 1);
+    if (!argv[i] || recv_all(fd, argv[i], (size_t)len)) goto done;
+  }
+  fflush(stdout); fflush(stderr);
+  save1 = dup(1); save2 = dup(2);
+  dup2(fds[0], 1); dup2(fds[1], 2);
+  if (chdir(cwd) != 0) { fprintf(stderr, "ERROR: cannot enter %s\n", cwd); status = 255; }
+  else {
+    optind = 0;                                       /* glibc: restart getopt from scratch */
+    serving = 1;
+    jr = setjmp(server_jmp);
+    if (jr == 0) status = grimm_main(argc, argv);
+    else status = jr - 1;
+    serving = 0;
+  }
+  fflush(stdout); fflush(stderr);
+  dup2(save1, 1); dup2(save2, 2);
+  close(save1); close(save2);
+done:
+  if (fds[0] >= 0) close(fds[0]);
+  if (fds[1] >= 0) close(fds[1]);
+  send_all(fd, &status, sizeof status);
+  if (argv) { for (i = 0; i < argc; i++) free(argv[i]); free(argv); }
+  free(cwd);
+}
+
+static int run_server(const char *path)
+{
+  struct sockaddr_un addr;
+  int ls, one[6] = {1, 2, 3, 1, -2, 3}, pair[2] = {0, 1};
+  grsr_stats_t st;
+  if (strlen(path) >= sizeof addr.sun_path) { fprintf(stderr, "ERROR: socket path too long\n"); return 255; }
+  /* create the CUDA context and load the kernels before the first request arrives */
+  if (grsr_dist_pairs(one, 2, 3, pair, 1, (int32_t *)&st, 5, first_device(), 1) != GRSR_OK) {
+    fprintf(stderr, "ERROR: %s\n", grsr_last_error());
+    return 255;
+  }
+  signal(SIGPIPE, SIG_IGN);
+  ls = socket(AF_UNIX, SOCK_STREAM, 0);
+  memset(&addr, 0, sizeof addr);
+  addr.sun_family = AF_UNIX;
+  strcpy(addr.sun_path, path);
+  unlink(path);
+  if (ls < 0 || bind(ls, (struct sockaddr *)&addr, sizeof addr) != 0 || listen(ls, 64) != 0) {
+    fprintf(stderr, "ERROR: cannot listen on %s: ", path);
+    perror("");
+    return 255;
+  }
+  fprintf(stderr, "grimm: resident on %s (GRSR_SERVER=%s grimm ... to use it)\n", path, path);
+  for (;;) {
+    int fd = accept(ls, NULL, NULL);
+    if (fd < 0) { if (errno == EINTR) continue; break; }
+    serve_one(fd);
+    close(fd);
+  }
+  return 0;
+}
+
+int main(int argc, char *argv[])
+{
+  const char *srv = getenv("GRSR_SERVER");
+  if (argc == 3 && strcmp(argv[1], "--server") == 0) return run_server(argv[2]);
+  if (srv && *srv) {
+    int status = run_remote(srv, argc, argv);
+    if (status >= 0) return status;
+  }
+  return grimm_main(argc, argv);
 }

@@ -6,6 +6,8 @@
 #include "grsr_scenario.cuh"
 #include "grsr_stepwise.cuh"
 #include "grsr_walk.cuh"
+#include "grsr_unsigned.cuh"
+#include "grsr_unsigned_host.hpp"
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -1084,6 +1086,79 @@ int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes, 
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dout, (size_t)ncand * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return GRSR_OK;
+}
+
+int grsr_unsigned_dist(const int32_t *g1, const int32_t *g2, int num_genes, int circular,
+                       int32_t *signed_g1, int32_t *signed_g2, grsr_unsigned_info_t *info, int device) {
+  int rc = check_device_range(device, 1);
+  if (rc) return rc;
+  if (!info) return fail(GRSR_ERR_INVALID, "null info");
+  if ((rc = check_genomes(g1, 1, num_genes)) || (rc = check_genomes(g2, 1, num_genes))) return rc;
+  const int n = num_genes;
+  Launch L;
+  grsr::pick_shape(n, env_int("GRSR_THREADS", 0), &L.threads, &L.ept);
+  L.smem = grsr::work_bytes(n, L.threads * L.ept, false) + grsr::unsigned_extra_bytes(n);
+  if (n > grsr::kMaxSmemGenes || 2 * n + 2 > 32767 || L.threads * L.ept < 2 * n + 2 || L.smem > smem_budget())
+    return fail(GRSR_ERR_TOOLARGE, "num_genes=%d: the unsigned distance keeps the graph on chip", n);
+  if (device < 0 || device >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", device);
+  DeviceGuard guard;
+  CK(cudaSetDevice(device));
+  DevCache &c = g_cache[device];
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  if (!c.stream) CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaStream_t st = c.stream;
+  void *dg1, *dpi, *dsx, *ddb, *dbest;
+  const size_t gb = (size_t)n * sizeof(int32_t);
+  if ((rc = cache_reserve(c, 0, gb, &dg1)) || (rc = cache_reserve(c, 1, gb, &dpi)) ||
+      (rc = cache_reserve(c, 2, gb, &dsx)) || (rc = cache_reserve(c, 3, 2 * gb, &ddb)) ||
+      (rc = cache_reserve(c, 6, sizeof(unsigned long long), &dbest)))
+    return rc;
+  int32_t *demit = (int32_t *)ddb + n;
+
+  // one pass of unsigned_mcdist's loop: all 2^k sign assignments on the device
+  auto eval = [&](const int32_t *gamma, grsr::UnsignedPass &P, int k, int &best_d,
+                  std::vector<int32_t> &best_pi) -> int {
+    const int m = (int)P.doubletons.size();
+    std::vector<int32_t> sidx((size_t)n, -1);
+    for (size_t j = 0; j < P.singletons.size(); j++) sidx[(size_t)P.singletons[j]] = (int32_t)j;
+    const unsigned long long leaves = 1ull << k;
+    unsigned long long best = ~0ull;
+    CK(cudaMemcpyAsync(dg1, gamma, gb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dpi, P.pi0.data(), gb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(dsx, sidx.data(), gb, cudaMemcpyHostToDevice, st));
+    if (m) CK(cudaMemcpyAsync(ddb, P.doubletons.data(), (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(dbest, 0xff, sizeof best, st));
+    Launch LL = L;
+    int r = 0;
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, r = finish_plan(grsr::unsigned_signs_kernel<kNt, kEpt>, (long long)leaves, LL));
+    if (r) return r;
+    GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::unsigned_signs_kernel<kNt, kEpt><<<LL.grid, LL.threads, LL.smem, st>>>(
+        (const int32_t *)dg1, (const int32_t *)dpi, (const int32_t *)dsx, (const int32_t *)ddb, n, k, m, 0ull, leaves,
+        (unsigned long long *)dbest, (int32_t *)nullptr)));
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&best, dbest, sizeof best, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int d = (int)(best >> 32);
+    if (d < best_d) {
+      const unsigned long long t = best & 0xFFFFFFFFull;
+      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::unsigned_signs_kernel<kNt, kEpt><<<1, LL.threads, LL.smem, st>>>(
+          (const int32_t *)dg1, (const int32_t *)dpi, (const int32_t *)dsx, (const int32_t *)ddb, n, k, m, t, 1ull,
+          (unsigned long long *)nullptr, demit)));
+      CK(cudaGetLastError());
+      best_pi.resize((size_t)n);
+      CK(cudaMemcpyAsync(best_pi.data(), demit, gb, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      best_d = d;
+    }
+    return GRSR_OK;
+  };
+  grsr::UnsignedResult R;
+  if ((rc = grsr::unsigned_distance(g1, g2, n, circular != 0, eval, R))) return rc;
+  info->dist = R.dist; info->approx = R.approx; info->passes = R.passes;
+  for (int q = 0; q < 2; q++) { info->num_sing[q] = R.num_sing[q]; info->num_doub[q] = R.num_doub[q]; }
+  if (signed_g1) memcpy(signed_g1, R.g1.data(), gb);
+  if (signed_g2) memcpy(signed_g2, R.g2.data(), gb);
   return GRSR_OK;
 }
 

@@ -422,7 +422,10 @@ __device__ inline int blk_compact_runs(int N, F f, VT *cache, VT *out, unsigned 
 #ifndef GRSR_SMALL_EXTENT
 #define GRSR_SMALL_EXTENT 48   // S4: extents up to this many vertices are scanned by one lane
 #endif
-template <class TM, class VT>
+// kComponentsOnly: stop after S6 -- on return A2[v] = cycle id, P[c] = component (root cycle) of cycle c,
+// P[comp + 1] = 1 if the component is oriented; h and f are not computed (returns 0).  Used by the
+// unsigned-distance kernel, which needs the components of sign_2strips (G/unsigned.c:958-1040).
+template <class TM, class VT, bool kComponentsOnly = false>
 __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
   const int tid = TM::tid(), nt = TM::size(), lane = tid & 31;
   const int S = wk.S;
@@ -563,6 +566,8 @@ __device__ inline unsigned hurdles_slow_path(WorkT<VT> &wk, int n) {
     if (A2[r] == r && (A1[r] & 1u)) W[W[r] + 1] = 1;
   }
   TM::sync();
+
+  if (kComponentsOnly) return 0;
 
   // S7 + S8: the vertices of unoriented components, in vertex order, as component ids (the filtered
   //     scan of G/graph_components.c:566-585); runs of equal ids = the reference's "blocks", one
@@ -711,7 +716,10 @@ __device__ inline bool unoriented_cycles_all_covered(WK &wk, int n, int S, WordF
 // an even graphdist (G/graph_edit.c:1165-1238) exactly when ORB[x] == ORB[y].
 // All threads of the block must call; all receive the result.
 // --------------------------------------------------------------------------------------------------
-template <int NT, int EPT, bool kKeepOrbits, class EndsFn>
+// kComponentsOnly (unsigned-distance kernel): b and c as usual; st.h = 1 means "the component analysis
+// ran (up to S6, see hurdles_slow_path) because some unoriented cycle may lie in an unoriented
+// component", st.h = 0 means every component is oriented; st.f and st.d are not meaningful.
+template <int NT, int EPT, bool kKeepOrbits, class EndsFn, bool kComponentsOnly = false>
 __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int S = wk.S;
@@ -828,8 +836,9 @@ __device__ inline Stats dist_core(Work &wk, int n, EndsFn ends) {
       if (cy == a) { W[a] = a; W[a + 1] = 0; }
     }
     __syncthreads();
-    unsigned hf = hurdles_slow_path<TeamBlock>(wk, n);
+    unsigned hf = hurdles_slow_path<TeamBlock, uint16_t, kComponentsOnly>(wk, n);
     st.h = (int)(hf >> 1); st.f = (int)(hf & 1u);
+    if (kComponentsOnly) st.h = 1;
   }
   GRSR_PHASE(0);
   st.d = st.b - st.c + st.h + st.f;

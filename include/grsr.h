@@ -123,6 +123,28 @@ int grsr_scenario_prefix(const int32_t *src, const int32_t *dst, int npairs, int
 int grsr_trial_distances(const int32_t *src, const int32_t *dst, int num_genes,
                          const int32_t *cands, int64_t ncand, int32_t *out, int device);
 
+/* unsigned_mcdist_nomem(g1, g2, num_genes, 0 chromosomes, circular, verbose, &dist_error)
+ * (G/unsigned.c:786-830, called at G/mcmain.c:810 for `grimm -u -g i,j` and, through
+ * set_unsigneddist_matrix, G/unsigned.c:1107-1131, for the -u matrix): the exact reversal distance of
+ * two UNSIGNED genomes -- the minimum of the signed distance over all signings -- by the reference's
+ * algorithm: strips of >= 2 genes signed canonically, every sign assignment of the singletons
+ * enumerated (at most 2^22, info->approx = 1 beyond that, as in the reference), 2-strips of
+ * unoriented components re-signed per assignment (G/unsigned.c:885-1095).  The 2^k evaluations run on
+ * the GPU.  The signs of g1 / g2 on input are ignored where the reference ignores them.
+ * signed_g1 / signed_g2 (may be NULL) receive the genomes with the optimal signs (for circular
+ * genomes also rotated / flipped the way the reference leaves them): the reference overwrites its
+ * input with these, so a following scenario sorts signed_g1 into signed_g2.  For linear genomes
+ * signed_g1 is g1 unchanged.  num_genes must fit the on-chip kernels. */
+typedef struct {
+  int32_t dist;         /* the unsigned reversal distance */
+  int32_t approx;       /* 1: more than 22 singletons, answer approximated (reference: dist_error) */
+  int32_t passes;       /* 1, or 2 for circular genomes without a common strip of 3 genes */
+  int32_t num_sing[2];  /* per pass: what -v prints as "Number of Singletons" */
+  int32_t num_doub[2];  /* per pass: "Number of 2-strips" */
+} grsr_unsigned_info_t;
+int grsr_unsigned_dist(const int32_t *g1, const int32_t *g2, int num_genes, int circular,
+                       int32_t *signed_g1, int32_t *signed_g2, grsr_unsigned_info_t *info, int device);
+
 /* ---- device-resident entry points (pointers are CUDA device pointers on the CURRENT device;
  *      stream is a cudaStream_t; no validation, no copies, asynchronous).  Up to
  *      grsr_max_genes_on_chip() genes a call takes its scratch from the device's stream-ordered

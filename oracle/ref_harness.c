@@ -17,6 +17,7 @@
 #include "mcrdist.h"
 #include "scenario.h"
 #include "opt_scenario.h"
+#include "unsigned.h"
 
 FILE *outfile; /* the global the reference prints to (defined in G/mcmain.c:66, which we leave out) */
 
@@ -156,4 +157,23 @@ int ref_scenario_prefix(const int *src, const int *dst, int n, int *steps, int c
   waitpid(pid, NULL, 0);
   free(line);
   return nsteps;
+}
+
+/* unsigned_mcdist_nomem (G/unsigned.c:786-830) on copies of the two genomes: returns the distance,
+ * out_g1 / out_g2 = the genomes as the reference leaves them (optimal signs, circular shifts),
+ * *approx = dist_error.  Not thread-safe (the reference prints through the global outfile). */
+int ref_unsigned_dist(const int *g1, const int *g2, int n, int circular, int *out_g1, int *out_g2, int *approx)
+{
+  struct genome_struct a, b;
+  int d, err = 0;
+  FILE *saved = outfile;
+  memset(&a, 0, sizeof a); memset(&b, 0, sizeof b);
+  memcpy(out_g1, g1, sizeof(int) * (size_t)n);
+  memcpy(out_g2, g2, sizeof(int) * (size_t)n);
+  a.genes = out_g1; b.genes = out_g2;
+  outfile = stderr;
+  d = unsigned_mcdist_nomem(&a, &b, n, 0, circular, 0, &err);
+  outfile = saved;
+  *approx = err;
+  return d;
 }

@@ -268,3 +268,21 @@ def normalise_report(text: str) -> str:
 def error_head(err: str) -> str:
     """The reference prints its error text, then a blank line and the usage screen: keep the text."""
     return err.split("\n\nGRIMM", 1)[0].rstrip("\n")
+
+
+def ref_unsigned(g1, g2, circular=False):
+    """(distance, signed g1, signed g2, approx) from the reference's unsigned_mcdist_nomem."""
+    a, b = _i32(g1), _i32(g2)
+    o1, o2 = np.zeros_like(a), np.zeros_like(b)
+    ap = ctypes.c_int(0)
+    d = reference().ref_unsigned_dist(_p(a), _p(b), len(a), 1 if circular else 0, _p(o1), _p(o2), ctypes.byref(ap))
+    return d, o1, o2, ap.value
+
+
+def emu_unsigned(g1, g2, circular=False, threads=0, grid=3):
+    a, b = _i32(g1), _i32(g2)
+    o1, o2 = np.zeros_like(a), np.zeros_like(b)
+    info = np.zeros(7, dtype=np.int32)
+    rc = emulator().emu_unsigned_dist(_p(a), _p(b), len(a), 1 if circular else 0, _p(o1), _p(o2), _p(info), threads, grid)
+    assert rc == 0
+    return int(info[0]), o1, o2, info

@@ -7,6 +7,8 @@
 #include "../../grsr_b200/csrc/grsr_scenario.cuh"
 #include "../../grsr_b200/csrc/grsr_stepwise.cuh"
 #include "../../grsr_b200/csrc/grsr_walk.cuh"
+#include "../../grsr_b200/csrc/grsr_unsigned.cuh"
+#include "../../grsr_b200/csrc/grsr_unsigned_host.hpp"
 #include <vector>
 
 extern "C" int emu_dist_pairs(const int32_t *genomes, int G, int n, const int32_t *pairs,
@@ -191,4 +193,44 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
     grsr::dist_deferred_kernel<kNt, kEpt>(genomes, sp, n, pairs, dlp, dcp, out, stride);
   }));
   return shared < 0 ? (int)((unsigned long long)flag * 64ull <= (unsigned long long)npairs) : 0;
+}
+
+// grsr_unsigned_dist as the library computes it (host preprocessing of grsr_unsigned_host.hpp + the
+// sign-enumeration kernel), with the kernel run through the emulator.  info7 = {dist, approx, passes,
+// num_sing[0..1], num_doub[0..1]}.
+extern "C" int emu_unsigned_dist(const int32_t *g1, const int32_t *g2, int n, int circular, int32_t *out_g1,
+                                 int32_t *out_g2, int32_t *info7, int threads, int grid) {
+  int t, e;
+  grsr::pick_shape(n, threads, &t, &e);
+  const size_t smem = grsr::work_bytes(n, t * e, false) + grsr::unsigned_extra_bytes(n);
+  auto eval = [&](const int32_t *gamma, grsr::UnsignedPass &P, int k, int &best_d, std::vector<int32_t> &best_pi) -> int {
+    const int m = (int)P.doubletons.size();
+    std::vector<int32_t> sidx((size_t)n, -1), emit((size_t)n, 0);
+    for (size_t j = 0; j < P.singletons.size(); j++) sidx[(size_t)P.singletons[j]] = (int32_t)j;
+    const unsigned long long leaves = 1ull << k;
+    unsigned long long best = ~0ull, *bp = &best;
+    const int32_t *pi0 = P.pi0.data(), *sx = sidx.data(), *db = P.doubletons.data();
+    GRSR_DISPATCH_SHAPE(t, e, emu::launch((unsigned)grid, (unsigned)t, smem, [&] {
+      grsr::unsigned_signs_kernel<kNt, kEpt>(gamma, pi0, sx, db, n, k, m, 0ull, leaves, bp, (int32_t *)nullptr);
+    }));
+    const int d = (int)(best >> 32);
+    if (d < best_d) {
+      const unsigned long long tt = best & 0xFFFFFFFFull;
+      int32_t *ep = emit.data();
+      GRSR_DISPATCH_SHAPE(t, e, emu::launch(1, (unsigned)t, smem, [&] {
+        grsr::unsigned_signs_kernel<kNt, kEpt>(gamma, pi0, sx, db, n, k, m, tt, 1ull, (unsigned long long *)nullptr, ep);
+      }));
+      best_pi = emit;
+      best_d = d;
+    }
+    return 0;
+  };
+  grsr::UnsignedResult R;
+  int rc = grsr::unsigned_distance(g1, g2, n, circular != 0, eval, R);
+  if (rc) return rc;
+  info7[0] = R.dist; info7[1] = R.approx; info7[2] = R.passes;
+  info7[3] = R.num_sing[0]; info7[4] = R.num_sing[1]; info7[5] = R.num_doub[0]; info7[6] = R.num_doub[1];
+  memcpy(out_g1, R.g1.data(), sizeof(int32_t) * (size_t)n);
+  memcpy(out_g2, R.g2.data(), sizeof(int32_t) * (size_t)n);
+  return 0;
 }

@@ -161,8 +161,34 @@ def main():
         with open(os.path.join(HERE, "cli", "in_%s.txt" % nm), "w") as f:
             f.write(txt)
         extra[nm] = "in_%s.txt" % nm
+    # unsigned genomes (-u): the reference's own demo inputs (data, copied)
+    # plus a seeded set of identity-with-a-few-reversals rows read as unsigned
+    import shutil
+    for nm, src in (("uns1", "unsigned1.txt"), ("uns3", "uns_3all.txt"), ("gollan", "gollan12.txt")):
+        shutil.copyfile(os.path.join(REF, "GRIMM", "GRIMM-2.01", "data", src), os.path.join(HERE, "cli", "in_%s.txt" % nm))
+        os.chmod(os.path.join(HERE, "cli", "in_%s.txt" % nm), 0o644)
+        extra[nm] = "in_%s.txt" % nm
+    rng_u = random.Random(23)
+    unsr = [list(range(1, 31))] + [[abs(x) for x in gen.k_reversal_perm(30, k, rng_u)] for k in (2, 3, 5, 6)]
+    write_genomes(os.path.join(HERE, "cli", "in_unsr.txt"), unsr)
+    extra["unsr"] = "in_unsr.txt"
     cases = list(CLI_CASES)
     cases += [
+        ("uns1_L_u", ["-f", "{uns1}", "-L", "-u"]),
+        ("uns1_L_u_g12", ["-f", "{uns1}", "-L", "-u", "-g", "1,2"]),
+        ("uns1_L_u_g13_v", ["-f", "{uns1}", "-L", "-u", "-g", "1,3", "-v"]),
+        ("uns1_C_u_v", ["-f", "{uns1}", "-C", "-u", "-v"]),
+        ("uns3_C_u", ["-f", "{uns3}", "-C", "-u"]),
+        ("uns3_L_u", ["-f", "{uns3}", "-L", "-u"]),
+        ("gollan_L_u_v", ["-f", "{gollan}", "-L", "-u", "-v"]),
+        ("gollan_C_u_g12_v", ["-f", "{gollan}", "-C", "-u", "-g", "1,2", "-v"]),
+        ("gollan_L_u_m", ["-f", "{gollan}", "-L", "-u", "-m"]),
+        ("gollan_L_u_g21_d", ["-f", "{gollan}", "-L", "-u", "-g", "2,1", "-d"]),
+        ("unsr_L_u", ["-f", "{unsr}", "-L", "-u"]),
+        ("unsr_C_u", ["-f", "{unsr}", "-C", "-u"]),
+        ("unsr_C_u_g23_v", ["-f", "{unsr}", "-C", "-u", "-g", "2,3", "-v"]),
+        ("unsr_L_u_g14_t1", ["-f", "{unsr}", "-L", "-u", "-g", "1,4", "-t", "1"]),
+        ("unsr_L_u_g52_S1", ["-f", "{unsr}", "-L", "-u", "-g", "5,2", "-S", "1"]),
         ("n120_C_m", ["-f", "{n120}", "-C", "-m"]),
         ("n120_L_g23_v", ["-f", "{n120}", "-L", "-g", "2,3", "-v"]),
         ("n120_C_g13", ["-f", "{n120}", "-C", "-g", "1,3"]),

@@ -76,6 +76,6 @@ def test_cli_refuses_out_of_scope_modes():
     grimm = build.build_cli()
     cli_dir = os.path.join(U.GOLDEN, "cli")
     f = os.path.join("..", "example_mgr_macro.txt")
-    for args in (["-f", f], ["-f", f, "-C", "-u"], ["-f", f, "-L", "-g", "1,2", "-t", "2"], ["-f", f, "-C", "-W", "x"]):
+    for args in (["-f", f], ["-f", f, "-C", "-U", "5"], ["-f", f, "-L", "-g", "1,2", "-t", "2"], ["-f", f, "-C", "-W", "x"]):
         rc, out, err = U.run_cli(grimm, args, cli_dir)
         assert rc == 255 and "outside the path" in err

@@ -47,3 +47,41 @@ def test_reptA_style_extraction(grimm):
     assert dist == ["20"]
     step1 = [ln for ln in out.splitlines() if ln.startswith("Step 1: ")][0]
     assert step1.split("[")[1].split("]")[0] == "4" and step1.split("[")[2].split("]")[0] == "4"
+
+
+def test_resident_mode_serves_the_same_reports(grimm, tmp_path):
+    """`grimm --server sock` keeps the CUDA context; GRSR_SERVER=sock grimm ... hands the invocation
+    (argv, cwd, stdout, stderr) to it.  Same text, same exit status -- including the error paths that
+    exit(-1) -- and a per-invocation wall time without the 0.4-1 s CUDA start-up."""
+    import subprocess
+    import time
+    sock = str(tmp_path / "grsr.sock")
+    srv = subprocess.Popen([grimm, "--server", sock], stderr=subprocess.PIPE)
+    try:
+        for _ in range(600):
+            if os.path.exists(sock):
+                break
+            assert srv.poll() is None, srv.stderr.read().decode()
+            time.sleep(0.05)
+        env = dict(os.environ, GRSR_SERVER=sock)
+        names = ["example_C_g12", "example_C_m_v", "err_dup", "example_C_g14", "nofile", "hurdles_L_g21_t1",
+                 "gollan_L_u_v", "example_C_g12", "messy_C_v"]
+        walls = []
+        for name in names:
+            case = next(c for c in CASES if c["name"] == name)
+            t0 = time.perf_counter()
+            r = subprocess.run([grimm] + case["args"], cwd=CLI_DIR, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            walls.append(time.perf_counter() - t0)
+            want_out = open(os.path.join(CLI_DIR, name + ".out")).read()
+            want_err = open(os.path.join(CLI_DIR, name + ".err")).read()
+            assert r.returncode == case["status"], (name, r.stderr.decode())
+            assert U.normalise_report(r.stdout.decode()) == U.normalise_report(want_out), name
+            assert U.error_head(r.stderr.decode()) == U.error_head(want_err), name
+        assert srv.poll() is None                      # error exits of requests did not end the server
+        assert min(walls) < 0.1, walls                 # no CUDA start-up per invocation
+    finally:
+        srv.kill()
+        srv.wait()
+    # nobody listening: the invocation runs in its own process
+    rc, out, _ = U.run_cli(grimm, ["-f", os.path.join("..", "example_mgr_macro.txt"), "-C", "-m"], CLI_DIR)
+    assert rc == 0 and "Distance Matrix" in out
