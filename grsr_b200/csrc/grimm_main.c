@@ -997,6 +997,15 @@ static int run_server(const char *path)
 int main(int argc, char *argv[])
 {
   const char *srv = getenv("GRSR_SERVER");
+  /* The CUDA driver initialises every visible GPU: 5.5 s on an 8-GPU B200 box against 0.5-1 s with one
+   * (profiles/r2_startup.txt).  Unless the caller asked for several devices or set the variable, only
+   * the device this process is going to use stays visible; it is then device 0. */
+  if (!getenv("CUDA_VISIBLE_DEVICES") && num_gpus() == 1) {
+    char one[16];
+    snprintf(one, sizeof one, "%d", first_device());
+    setenv("CUDA_VISIBLE_DEVICES", one, 1);
+    setenv("GRSR_DEVICE", "0", 1);
+  }
   if (argc == 3 && strcmp(argv[1], "--server") == 0) return run_server(argv[2]);
   if (srv && *srv) {
     int status = run_remote(srv, argc, argv);

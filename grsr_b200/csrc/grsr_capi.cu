@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -465,6 +467,12 @@ struct DeviceGuard {
 // mapping).  False when the two devices cannot do that.
 bool peer_ok(int dev, int owner) {
   if (dev == owner) return true;
+  static std::mutex mu;
+  static signed char known[kMaxDevices][kMaxDevices] = {};   // 0 unknown, 1 enabled, -1 impossible
+  if (dev < 0 || owner < 0 || dev >= kMaxDevices || owner >= kMaxDevices) return false;
+  std::lock_guard<std::mutex> lk(mu);
+  if (known[dev][owner]) return known[dev][owner] > 0;
+  known[dev][owner] = -1;
   int can = 0;
   if (cudaDeviceCanAccessPeer(&can, dev, owner) != cudaSuccess || !can) { cudaGetLastError(); return false; }
   int cur = -1;
@@ -472,8 +480,9 @@ bool peer_ok(int dev, int owner) {
   if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return false; }
   cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
   if (cur >= 0) cudaSetDevice(cur);
-  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return true; }
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); known[dev][owner] = 1; return true; }
   if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  known[dev][owner] = 1;
   return true;
 }
 
@@ -528,18 +537,65 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
   return validation_error(err, genomes, n);
 }
 
+// Persistent host threads for the multi-device calls: creating N - 1 threads per call costs ~25 us each,
+// one after the other, which is a quarter of a millisecond before the last device even starts -- as much
+// as a third of the kernel time of an 8-way matrix.  Workers sleep on a condition variable between calls.
+struct WorkerPool {
+  std::mutex call_mu;                 // one multi-device call at a time
+  std::mutex mu;
+  std::condition_variable cv_go, cv_done;
+  std::vector<std::thread> threads;
+  std::function<void(int)> fn;
+  int gen = 0, want = 0, left = 0;
+  void start(int nworkers, std::function<void(int)> f) {
+    std::unique_lock<std::mutex> lk(mu);
+    while ((int)threads.size() < nworkers) {
+      const int id = (int)threads.size() + 1;
+      threads.emplace_back([this, id] { loop(id); });
+    }
+    fn = std::move(f); want = nworkers; left = nworkers; gen++;
+    cv_go.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_done.wait(lk, [&] { return left == 0; });
+  }
+  void loop(int id) {
+    int seen = 0;
+    for (;;) {
+      std::function<void(int)> f;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_go.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+        if (id > want) continue;
+        f = fn;
+      }
+      f(id);
+      std::lock_guard<std::mutex> lk(mu);
+      if (--left == 0) cv_done.notify_all();
+    }
+  }
+};
+WorkerPool &worker_pool() { static WorkerPool *p = new WorkerPool; return *p; }   // never destroyed: its threads outlive main
+
 // Runs work(d) for d = 0 .. ngpus-1, device first_device + d: d = 0 on the calling thread, the others
-// on one host thread each; the first error (lowest device) is reported.
+// on the pool's threads; the first error (lowest device) is reported.
 template <class F>
 int on_devices(int first_device, int ngpus, F work) {
   std::vector<int> rcs(ngpus, 0);
   std::vector<std::string> errs(ngpus);
-  std::vector<std::thread> th;
-  for (int d = 1; d < ngpus; d++)
-    th.emplace_back([&, d]() { rcs[d] = work(d); if (rcs[d]) errs[d] = g_err; });
-  rcs[0] = work(0);
-  if (rcs[0]) errs[0] = g_err;
-  for (auto &t : th) t.join();
+  if (ngpus > 1) {
+    WorkerPool &pool = worker_pool();
+    std::lock_guard<std::mutex> one_call(pool.call_mu);
+    pool.start(ngpus - 1, [&](int d) { rcs[d] = work(d); if (rcs[d]) errs[d] = g_err; });
+    rcs[0] = work(0);
+    if (rcs[0]) errs[0] = g_err;
+    pool.wait();
+  } else {
+    rcs[0] = work(0);
+    if (rcs[0]) errs[0] = g_err;
+  }
   for (int d = 0; d < ngpus; d++) {
     if (!rcs[d]) continue;
     if (ngpus == 1) return fail(rcs[d], "%s", errs[d].c_str());

@@ -24,8 +24,9 @@
 //            (G/graph_edit.c:207-457) with ~1.4 * 2n/32 steps per lane and ~100 walks per pair.
 //   jumping  pointer jumping over the walk words only (registers, like dist_core's phase B); the
 //            walk whose own segment holds the orbit minimum is the orbit's root.
-//   rest     vertices never claimed lie on orbits without a node (short cycles): each walks its orbit
-//            until it meets a smaller vertex; the one that gets round is the root.
+//   rest     vertices never claimed lie on orbits without a node (short cycles): the lane that finds one
+//            in its part of H walks its orbit until it meets a smaller vertex; the one that gets round is
+//            the root.
 //   result   c = number of roots with an even label; when no root is unoriented every component is
 //            oriented and d = b - c (the early exit of G/graph_components.c:522-527).  Unoriented
 //            cycles first get the cheap "covered by an oriented cycle" test of dist_core; a pair it
@@ -65,13 +66,8 @@ __host__ __device__ inline int walk_shift(int n) {
 // kernel argument: node stride and start threshold in one int
 __host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return shift | (idle_min << 8); }
 
-// 32-bit words of H: n+2 used (entries 0 .. 2n+2), padded so that 32 lanes x 16-byte loads cover it in
-// whole rounds and at least 32 words (64 entries) stay free behind the used part: the list of
-// unclaimed vertices of the leftover phase lives there.
-__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 32 + 127) & ~127; }
-// entries of H (16-bit) that hold the leftover list: [2n+3, 2 * hwords), taken from the word boundary
-__host__ __device__ inline int walk_list_first(int n) { return (2 * n + 3 + 1) & ~1; }
-__host__ __device__ inline int walk_list_cap(int n) { return 2 * walk_hwords(n) - walk_list_first(n); }
+// 32-bit words of H: n+2 used (entries 0 .. 2n+2), padded so that 32 lanes x 16-byte loads cover it in whole rounds
+__host__ __device__ inline int walk_hwords(int n) { return (n + 2 + 127) & ~127; }
 
 // shared memory of one warp: tail u16[n+1] | H u16[2 * hwords] | walk words u32[128] | MAP u8[256] | misc
 __host__ __device__ inline size_t walk_tail_bytes(int n) { return (((size_t)(n + 1) * 2) + 15) & ~(size_t)15; }
@@ -206,9 +202,12 @@ __device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
 
 // One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
 // in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
-__device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
-                                 int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
-                                 int32_t *defer_list, unsigned *defer_count) {
+// may_retry: a pair that only ran out of room (walk words used up, so that long stretches stay unclaimed and
+// the leftover budget runs out) is NOT deferred; the function returns 2 and the caller runs it again with a
+// coarser node stride.  Returns 1 for a deferred pair.
+__device__ inline int walk_pair_once(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
+                                     int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
+                                     int32_t *defer_list, unsigned *defer_count, bool may_retry) {
   const int shift = shape & 0xFF, idle_min = shape >> 8;   // node stride 2^shift; lanes out of work before new walks start
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -360,17 +359,14 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   unsigned ncyc = 0, nun = 0;
   walk_jump<4>(NW, UL, W, lane, ncyc, nun);
 
-  // ---- orbits without a node: list the unclaimed vertices, then one lane per vertex ---------------
-  // The list lives in the free entries behind the used part of H; its entries carry bit 15, so the scan
-  // that fills it (whole rows of H, padding included) takes them for claimed entries.
+  // ---- orbits without a node: the scan of H finds the unclaimed vertices, the lane that finds one ----
+  // walks its orbit at once (H is only read from here on): until it meets a smaller vertex, or gets
+  // round -- then it is the root of that orbit.
   int defer = 0;
   {
-    uint16_t *LL = H + walk_list_first(n);
-    const unsigned llcap = (unsigned)walk_list_cap(n);
-    if (lane == 0) UL[31] = 0;
-    __syncwarp();
     const uint4 *H4 = (const uint4 *)Hw;
     const int hq = hwords >> 2;
+    int budget = kWalkLeftoverBudget;
     for (int q = lane; q < hq; q += 32) {                // hq is a multiple of 32: whole rounds
       const uint4 x = H4[q];
       const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
@@ -384,34 +380,24 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
           while (um) {
             const int k = __ffs((int)um) - 1;
             um &= um - 1u;
-            const unsigned pos = atomicAdd(&UL[31], 1u);
-            if (pos < llcap) LL[pos] = (uint16_t)((((unsigned)(8 * q + k) - 1u)) | kVis);  // vertex of entry 8q+k
-          }
-        }
-      }
-    }
-    __syncwarp();
-    const unsigned cnt = UL[31];
-    if (cnt > llcap) defer = 1;
-    else {
-      int budget = kWalkLeftoverBudget;
-      for (unsigned i = lane; i < cnt; i += 32) {
-        const unsigned u0 = LL[i] & 0x7FFFu;
-        unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
-        bool root = true;
-        while (x1 != u0) {
-          if (x1 < u0) { root = false; break; }                  // a smaller vertex owns this orbit
-          if (--budget < 0) { root = false; defer = 1; break; }
-          const unsigned nx = H[x1 + 1] & 0x7FFFu;
-          orr |= x1 ^ nx;
-          x1 = nx;
-        }
-        if (root && !(u0 & 1u)) {
-          ncyc++;
-          if (!(orr & 1u)) {
-            nun++;
-            const unsigned kk = atomicAdd(&UL[0], 1u);
-            if (kk < (unsigned)kWalkMaxUnoriented) UL[1 + kk] = u0;
+            const unsigned u0 = (unsigned)(8 * q + k) - 1u;       // vertex of entry 8q+k
+            unsigned x1 = H[u0 + 1] & 0x7FFFu, orr = u0 ^ x1;
+            bool root = true;
+            while (x1 != u0) {
+              if (x1 < u0) { root = false; break; }                // a smaller vertex owns this orbit
+              if (--budget < 0) { root = false; defer = 1; break; }
+              const unsigned nx = H[x1 + 1] & 0x7FFFu;
+              orr |= x1 ^ nx;
+              x1 = nx;
+            }
+            if (root && !(u0 & 1u)) {
+              ncyc++;
+              if (!(orr & 1u)) {
+                nun++;
+                const unsigned kk = atomicAdd(&UL[0], 1u);
+                if (kk < (unsigned)kWalkMaxUnoriented) UL[1 + kk] = u0;
+              }
+            }
           }
         }
       }
@@ -422,6 +408,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   nun = __reduce_add_sync(kFull, nun);
   defer = __any_sync(kFull, defer);
   __syncwarp();
+  if (defer && may_retry) return 2;                   // out of room: nothing was decided about this pair
   const int b = (n + 1) - (int)nadj, c = (int)ncyc;
 
   // ---- unoriented cycles: the "covered by an oriented cycle" test of dist_core -------------------
@@ -464,6 +451,17 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   return defer != 0;
 }
 
+// One pair by one warp.  A pair whose walks outgrow the per-warp tables (about 1 in 400 random pairs of
+// 2000 genes) is run once more with twice the node stride -- half as many possible walk starts, so the
+// tables suffice -- instead of being sent to the block-per-pair kernel.
+__device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
+                                 int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
+                                 int32_t *defer_list, unsigned *defer_count) {
+  int r = walk_pair_once(wm, genomes, n, gi, pj, p, out, stride, shape, defer_list, defer_count, true);
+  if (r == 2) r = walk_pair_once(wm, genomes, n, gi, pj, p, out, stride, shape + 1, defer_list, defer_count, false);
+  return r != 0;
+}
+
 // A warp that had to defer every one of its first kWalkGiveUp pairs stops trying: on a batch of
 // hurdle-rich pairs the first tier then costs a few per cent instead of its full time on top of the
 // second tier's.  The rest of its pairs go to the deferred list unseen.
@@ -482,12 +480,18 @@ __device__ inline bool walk_list_sorted(const unsigned *changes, long long npair
   return (unsigned long long)*changes * 64ull <= (unsigned long long)npairs;
 }
 
-// Work distribution of both kernels: a zero-initialised global ticket hands out chunks of
-// consecutive pairs, so a warp (block) that drew cheap pairs simply draws more -- no static split
-// whose slowest part the launch has to wait for.  chunk = pairs per ticket (>= 1).
-__host__ __device__ inline int walk_chunk(long long npairs, long long takers, int lo, int hi) {
-  long long c = npairs / (takers * 8);                // about 8 tickets per taker
-  return (int)(c < lo ? lo : (c > hi ? hi : c));
+// Work distribution of both kernels: guided self-scheduling over one zero-initialised global counter of
+// pairs.  A taker (a warp, or a block of the shared-row kernel) claims the next `chunk` pairs, where
+// chunk = what is left / (2 x takers), at least `lo`: large chunks while there is plenty of work (few
+// claims, few block barriers), single pairs per warp at the end (nobody waits long for the slowest).
+__device__ inline long long walk_claim(unsigned *next, long long npairs, long long takers, int lo,
+                                       long long *count) {
+  const long long seen = (long long)*(volatile unsigned *)next;
+  long long c = (npairs - seen) / (2 * takers);
+  if (c < lo) c = lo;
+  const long long start = (long long)atomicAdd(next, (unsigned)c);
+  *count = c;
+  return start;
 }
 
 // One warp, one pair at a time, every warp with its own staged pi row: a warp draws chunks of
@@ -510,14 +514,13 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   if (lane == 0) tail[n] = (uint16_t)(2 * n + 1);     // the sentinel gene's entry
   __syncwarp();
 
-  const int chunk = walk_chunk(npairs, (long long)gridDim.x * wpb, 1, 8);
   int staged = -1;
   WalkQuota quota = {0, 0};
   for (;;) {
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1u);
-    t = __shfl_sync(kFull, t, 0);
-    const long long p0 = (long long)t * chunk;
+    long long p0 = 0, chunk = 0;
+    if (lane == 0) p0 = walk_claim(ticket, npairs, (long long)gridDim.x * wpb, 1, &chunk);
+    p0 = __shfl_sync(kFull, p0, 0);
+    chunk = __shfl_sync(kFull, chunk, 0);
     if (p0 >= npairs) break;
     const long long p1 = (p0 + chunk < npairs) ? p0 + chunk : npairs;
     for (long long p = p0; p < p1; p++) {
@@ -549,7 +552,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   if (order_flag && !walk_list_sorted(order_flag, npairs)) return;  // not sorted: the private-row kernel runs
   GRSR_DYN_SMEM(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  unsigned *s_ctl = (unsigned *)smem_raw;             // first 16 bytes: [0] run length, [1] next pair of the run, [2] ticket
+  unsigned *s_ctl = (unsigned *)smem_raw;             // first 16 bytes: [0] run length, [1] next pair of the run, [2] chunk start, [3] chunk length
   uint16_t *tail = (uint16_t *)(smem_raw + 16);
   WalkMem wm;
   wm.tail = tail;
@@ -558,15 +561,19 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n + 1);
 
   WalkQuota quota = {0, 0};
-  const int chunk = walk_chunk(npairs, gridDim.x, wpb, 8 * wpb);
   int staged = -1;
   for (;;) {
     __syncthreads();                                   // everybody is done with the previous chunk
-    if (threadIdx.x == 0) s_ctl[2] = atomicAdd(ticket, 1u);
+    if (threadIdx.x == 0) {
+      long long c;
+      const long long st = walk_claim(ticket, npairs, gridDim.x, wpb, &c);
+      s_ctl[2] = (unsigned)(st < npairs ? st : npairs);
+      s_ctl[3] = (unsigned)c;
+    }
     __syncthreads();
-    const long long b0 = (long long)s_ctl[2] * chunk;
+    const long long b0 = (long long)s_ctl[2];
     if (b0 >= npairs) break;
-    const long long b1 = (b0 + chunk < npairs) ? b0 + chunk : npairs;
+    const long long b1 = (b0 + (long long)s_ctl[3] < npairs) ? b0 + (long long)s_ctl[3] : npairs;
     for (long long p = b0; p < b1;) {
       const int pj = pairs[2 * p + 1];
       const unsigned left = (unsigned)(b1 - p);

@@ -47,3 +47,14 @@ def test_grimm_synteny_with_the_shim_reproduces_the_example(tmp_path):
     assert _strip(got["report.txt"]) == _strip(open(SHIPPED).read())
     # the blocks it hands to GRIMM are the hot path's own example input
     assert got["mgr_macro.txt"] == open(U.EXAMPLE).read()
+
+
+CHECK = os.path.join(U.ROOT, "oracle", "_ref", "synteny_matrix_check")
+
+
+@pytest.mark.skipif(not os.path.exists(CHECK), reason="oracle/_ref/synteny_matrix_check not built")
+def test_shim_batched_matrix_and_single_pair_equal_the_reference_function():
+    """gs_grsr_micro_matrix (one GPU call per block) and the wrapped mcdist_noncircular (one per pair)
+    against the reference's own mcdist_noncircular linked into the same program (oracle/synteny_matrix_check.c)."""
+    r = subprocess.run([CHECK], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK 60"), r.stdout + r.stderr
