@@ -199,7 +199,7 @@ int plan_walk(K kernel, bool shared, int n, long long npairs, WalkPlan &P) {
   if (fs >= P.shift && fs <= 10) P.shift = fs;
   int idle = env_int("GRSR_WALK_IDLE", grsr::kWalkIdle);
   if (idle < 1 || idle > 32) idle = grsr::kWalkIdle;
-  P.shift = grsr::walk_shape_arg(P.shift, idle);
+  P.shift = grsr::walk_shape_arg(P.shift, idle) | ((env_int("GRSR_WALK_GUIDE4", 0) & 0xFF) << 16);
   P.wpb = best_wpb;
   P.smem = shared ? 16 + grsr::walk_tail_bytes(n) + grsr::walk_private_bytes(n) * best_wpb
                   : grsr::walk_warp_bytes(n) * best_wpb;
@@ -739,9 +739,10 @@ int stepwise_prefix(DevCache &c, cudaStream_t st, int32_t *d_src, const int32_t 
   return GRSR_OK;
 }
 
-// One device's part of a scenario call: copy all pairs in, run the persistent kernel on the queue.
+// One device's part of a scenario call: copy all pairs in (or, mapped = true, read them where they are:
+// page-locked host memory every device maps), run the persistent kernel on the queue.
 int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npairs, int n,
-                       const ScenOut &O, int max_steps, grsr::PairQueue queue, bool stepwise) {
+                       const ScenOut &O, int max_steps, grsr::PairQueue queue, bool stepwise, bool mapped) {
   if (dev < 0 || dev >= kMaxDevices) return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev);
   CK(cudaSetDevice(dev));
   DevCache &c = g_cache[dev];
@@ -770,11 +771,13 @@ int scenario_on_device(int dev, const int32_t *src, const int32_t *dst, int npai
                     grsr::scen_large_bytes(n), dev, LP);
   }
   if (rc) return rc;
-  void *dsrc, *ddst;
-  size_t gbytes = (size_t)npairs * n * sizeof(int32_t);
-  if ((rc = cache_reserve(c, 0, gbytes, &dsrc)) || (rc = cache_reserve(c, 1, gbytes, &ddst))) return rc;
-  CK(cudaMemcpyAsync(dsrc, src, gbytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ddst, dst, gbytes, cudaMemcpyHostToDevice, st));
+  void *dsrc = (void *)src, *ddst = (void *)dst;
+  if (!mapped) {
+    size_t gbytes = (size_t)npairs * n * sizeof(int32_t);
+    if ((rc = cache_reserve(c, 0, gbytes, &dsrc)) || (rc = cache_reserve(c, 1, gbytes, &ddst))) return rc;
+    CK(cudaMemcpyAsync(dsrc, src, gbytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ddst, dst, gbytes, cudaMemcpyHostToDevice, st));
+  }
   int resume = 0;
   if (stepwise && small) {
     if ((rc = stepwise_prefix(c, st, (int32_t *)dsrc, (const int32_t *)ddst, npairs, n, O, max_steps, L)))
@@ -813,8 +816,16 @@ int scenario_call(const int32_t *src, const int32_t *dst, int npairs, int n, grs
   const size_t ms = (size_t)(max_steps > 0 ? max_steps : 1);
   const size_t sbytes = (((size_t)npairs * ms * 2 * sizeof(int32_t)) + 15) & ~(size_t)15;
   const size_t ibytes = (((size_t)npairs * sizeof(int32_t)) + 15) & ~(size_t)15;
+  // Several devices: a pair is read ONCE, by whichever device draws it, so the genomes are not copied to
+  // every device (N x the whole batch through the host's staging buffers) but placed in the page-locked
+  // arena, which every device maps, by the pool's threads in parallel; the kernels read them over PCIe
+  // (12n bytes per pair against milliseconds of work).
+  const bool stepwise_call = npairs <= env_int("GRSR_STEPWISE_MAX", 16);
+  const bool mapped = ngpus > 1 && !stepwise_call && !env_int("GRSR_NO_MAPPED_INPUT", 0);
+  const size_t obytes = sbytes + 2 * ibytes + ((((size_t)npairs * sizeof(unsigned long long)) + 15) & ~(size_t)15);
+  const size_t gbytes_all = (((size_t)npairs * n * sizeof(int32_t)) + 15) & ~(size_t)15;
   void *base;
-  if ((rc = g_arena.reserve(sbytes + 2 * ibytes + (size_t)npairs * sizeof(unsigned long long), &base))) return rc;
+  if ((rc = g_arena.reserve(obytes + (mapped ? 2 * gbytes_all : 0), &base))) return rc;
   ScenOut O;
   O.steps = (int32_t *)base;
   O.nsteps = (int32_t *)((char *)base + sbytes);
@@ -822,8 +833,19 @@ int scenario_call(const int32_t *src, const int32_t *dst, int npairs, int n, grs
   O.evals = (unsigned long long *)((char *)base + sbytes + 2 * ibytes);
   memset(O.nsteps, 0, 2 * ibytes + (size_t)npairs * sizeof(unsigned long long));
 
+  const int32_t *ksrc = src, *kdst = dst;
+  if (mapped) {
+    int32_t *msrc = (int32_t *)((char *)base + obytes), *mdst = (int32_t *)((char *)base + obytes + gbytes_all);
+    on_devices(first_device, ngpus, [&](int d) -> int {
+      const size_t lo = (size_t)npairs * d / ngpus * n, hi = (size_t)npairs * (d + 1) / ngpus * n;
+      memcpy(msrc + lo, src + lo, (hi - lo) * sizeof(int32_t));
+      memcpy(mdst + lo, dst + lo, (hi - lo) * sizeof(int32_t));
+      return GRSR_OK;
+    });
+    ksrc = msrc; kdst = mdst;
+  }
   CK(cudaSetDevice(first_device));
-  const bool stepwise = npairs <= env_int("GRSR_STEPWISE_MAX", 16);
+  const bool stepwise = stepwise_call;
   if (stepwise) ngpus = 1;                              // a handful of pairs: one device, whole-GPU steps
   bool peers = true;
   for (int d = 1; d < ngpus; d++) peers = peers && peer_ok(first_device + d, first_device);
@@ -852,7 +874,7 @@ int scenario_call(const int32_t *src, const int32_t *dst, int npairs, int n, grs
         CK(cudaMemsetAsync(own, 0, 256, g_cache[dev].stream)); }
       q.ticket = (unsigned int *)own; q.first = d; q.stride = ngpus;
     }
-    return scenario_on_device(first_device + d, src, dst, npairs, n, O, max_steps, q, stepwise);
+    return scenario_on_device(first_device + d, ksrc, kdst, npairs, n, O, max_steps, q, stepwise, mapped);
   });
   if (rc) return rc;
   for (int p = 0; p < npairs; p++) {

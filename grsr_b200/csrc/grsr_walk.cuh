@@ -52,6 +52,7 @@ static const int kWalkMaxNodes = 256;        // nodes (possible walk starts) per
 static const int kWalkMaxWalks = 128;        // walks per pair (4 words per lane in the jumping phase; ids fit a byte)
 static const int kWalkGroup = 8;             // tau steps between two votes
 static const int kWalkIdle = 8;              // default: lanes that must be out of work before new walks start
+static const int kWalkGuide4 = 6;            // guided self-scheduling: a claim takes remaining / (kWalkGuide4 / 4 x takers)
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
 static const int kWalkLeftoverBudget = 1536; // steps a lane may spend on orbits without a node
 
@@ -202,13 +203,10 @@ __device__ inline void walk_init_private(WalkMem &wm, int n, int lane) {
 
 // One pair by one warp (all 32 lanes call): gamma = row gi of the genome table, pi = the row staged
 // in wm.tail.  stride 1: out[p] = d; stride 5: {d,b,c,h,f}; a deferred pair is appended to defer_list.
-// may_retry: a pair that only ran out of room (walk words used up, so that long stretches stay unclaimed and
-// the leftover budget runs out) is NOT deferred; the function returns 2 and the caller runs it again with a
-// coarser node stride.  Returns 1 for a deferred pair.
-__device__ inline int walk_pair_once(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
-                                     int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
-                                     int32_t *defer_list, unsigned *defer_count, bool may_retry) {
-  const int shift = shape & 0xFF, idle_min = shape >> 8;   // node stride 2^shift; lanes out of work before new walks start
+__device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
+                                 int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
+                                 int32_t *defer_list, unsigned *defer_count) {
+  const int shift = shape & 0xFF, idle_min = (shape >> 8) & 0xFF;   // node stride 2^shift; lanes out of work before new walks start
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int S = 2 * n + 2;
@@ -408,7 +406,6 @@ __device__ inline int walk_pair_once(const WalkMem &wm, const int32_t *__restric
   nun = __reduce_add_sync(kFull, nun);
   defer = __any_sync(kFull, defer);
   __syncwarp();
-  if (defer && may_retry) return 2;                   // out of room: nothing was decided about this pair
   const int b = (n + 1) - (int)nadj, c = (int)ncyc;
 
   // ---- unoriented cycles: the "covered by an oriented cycle" test of dist_core -------------------
@@ -451,17 +448,6 @@ __device__ inline int walk_pair_once(const WalkMem &wm, const int32_t *__restric
   return defer != 0;
 }
 
-// One pair by one warp.  A pair whose walks outgrow the per-warp tables (about 1 in 400 random pairs of
-// 2000 genes) is run once more with twice the node stride -- half as many possible walk starts, so the
-// tables suffice -- instead of being sent to the block-per-pair kernel.
-__device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ genomes, int n, int gi,
-                                 int pj, long long p, int32_t *__restrict__ out, int stride, int shape,
-                                 int32_t *defer_list, unsigned *defer_count) {
-  int r = walk_pair_once(wm, genomes, n, gi, pj, p, out, stride, shape, defer_list, defer_count, true);
-  if (r == 2) r = walk_pair_once(wm, genomes, n, gi, pj, p, out, stride, shape + 1, defer_list, defer_count, false);
-  return r != 0;
-}
-
 // A warp that had to defer every one of its first kWalkGiveUp pairs stops trying: on a batch of
 // hurdle-rich pairs the first tier then costs a few per cent instead of its full time on top of the
 // second tier's.  The rest of its pairs go to the deferred list unseen.
@@ -484,10 +470,11 @@ __device__ inline bool walk_list_sorted(const unsigned *changes, long long npair
 // pairs.  A taker (a warp, or a block of the shared-row kernel) claims the next `chunk` pairs, where
 // chunk = what is left / (2 x takers), at least `lo`: large chunks while there is plenty of work (few
 // claims, few block barriers), single pairs per warp at the end (nobody waits long for the slowest).
-__device__ inline long long walk_claim(unsigned *next, long long npairs, long long takers, int lo,
+// guide4 = 4 x the divisor per taker (6: claim two thirds of an even share of what is left; measured best of 4..32)
+__device__ inline long long walk_claim(unsigned *next, long long npairs, long long takers, int lo, int guide4,
                                        long long *count) {
   const long long seen = (long long)*(volatile unsigned *)next;
-  long long c = (npairs - seen) / (2 * takers);
+  long long c = 4 * (npairs - seen) / (guide4 * takers);
   if (c < lo) c = lo;
   const long long start = (long long)atomicAdd(next, (unsigned)c);
   *count = c;
@@ -518,7 +505,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   WalkQuota quota = {0, 0};
   for (;;) {
     long long p0 = 0, chunk = 0;
-    if (lane == 0) p0 = walk_claim(ticket, npairs, (long long)gridDim.x * wpb, 1, &chunk);
+    if (lane == 0) p0 = walk_claim(ticket, npairs, (long long)gridDim.x * wpb, 1, kWalkGuide4, &chunk);
     p0 = __shfl_sync(kFull, p0, 0);
     chunk = __shfl_sync(kFull, chunk, 0);
     if (p0 >= npairs) break;
@@ -566,7 +553,8 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
     __syncthreads();                                   // everybody is done with the previous chunk
     if (threadIdx.x == 0) {
       long long c;
-      const long long st = walk_claim(ticket, npairs, gridDim.x, wpb, &c);
+      const int g4 = (shape >> 16) & 0xFF;
+      const long long st = walk_claim(ticket, npairs, gridDim.x, wpb, g4 ? g4 : kWalkGuide4, &c);
       s_ctl[2] = (unsigned)(st < npairs ? st : npairs);
       s_ctl[3] = (unsigned)c;
     }

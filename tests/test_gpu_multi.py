@@ -137,7 +137,13 @@ def test_multi_gpu_scenario_queue(no_peer):
         srcs = np.array(srcs, dtype=np.int32); dsts = np.array(dsts, dtype=np.int32)
         want = [U.orc_scenario(s, d)[0] for s, d in zip(srcs, dsts)]
         for ng in sorted({2, _ndev()}):
-            got = capi.scenario_batch(srcs, dsts, ngpus=ng)
+            got = capi.scenario_batch(srcs, dsts, ngpus=ng)      # inputs read from the mapped host arena
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), ng
+            os.environ["GRSR_NO_MAPPED_INPUT"] = "1"             # inputs copied to every device instead
+            try:
+                got = capi.scenario_batch(srcs, dsts, ngpus=ng)
+            finally:
+                os.environ.pop("GRSR_NO_MAPPED_INPUT", None)
             assert all(np.array_equal(a, b) for a, b in zip(got, want)), ng
             pre, done, _ = capi.scenario_prefix(srcs, dsts, 7, ngpus=ng)
             assert all(np.array_equal(a, b[:7]) for a, b in zip(pre, want)), ng
