@@ -456,7 +456,9 @@ def config4_leg(capi, ngpus, no_cpu=False):
     n, k, cap = CONFIG4_GENES, CONFIG4_PAIRS, CONFIG4_STEP_CAP
     src = config4_sources(k)
     dst = np.tile(np.arange(1, n + 1, dtype=np.int32), (k, 1))
-    capi.scenario_prefix(src[:64 * ngpus], dst[:64 * ngpus], 1, ngpus=ngpus)       # warm-up: contexts, buffers
+    # warm-up: the same call once (contexts on all devices, peer mappings, the library's grow-only device
+    # buffers and its page-locked host arena reach their size, worker threads exist)
+    capi.scenario_prefix(src, dst, cap, ngpus=ngpus)
     t0 = time.perf_counter()
     steps, done, evals = capi.scenario_prefix(src, dst, cap, ngpus=ngpus)
     dt = time.perf_counter() - t0
