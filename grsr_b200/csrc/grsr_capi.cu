@@ -719,14 +719,21 @@ int stepwise_prefix(DevCache &c, cudaStream_t st, int32_t *d_src, const int32_t 
     int32_t *cur_p = d_src + (size_t)p * n;
     const int32_t *dst_p = d_dst + (size_t)p * n;
     int32_t *steps_p = O.steps + 2 * (size_t)p * max_steps;
+    // Eight batches are queued between two looks at the state: the three kernels are idempotent once the
+    // pair is sorted, out of steps or stuck, and keep making correct (filtered, one-candidate) steps if the
+    // last hurdle goes mid-way, so running a few rounds too many only costs their launch -- while a host
+    // round trip per batch was most of a cheap step's time.
+    const int kBatchesPerSync = 8;
     for (;;) {
-      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::step_prepare_kernel<kNt, kEpt><<<1, L.threads, L.smem, st>>>(
-          cur_p, dst_p, n, (grsr::StepState *)dstate, (int32_t *)dcands, cap)));
-      GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<LT.grid, LT.threads, LT.smem, st>>>(
-          cur_p, dst_p, n, (const int32_t *)dcands, 0LL, (int32_t *)dd2, ncand_dev)));
-      grsr::step_select_kernel<<<1, 256, 0, st>>>(cur_p, n, (grsr::StepState *)dstate,
-                                                  (const int32_t *)dcands, (const int32_t *)dd2,
-                                                  steps_p, max_steps);
+      for (int rep = 0; rep < kBatchesPerSync; rep++) {
+        GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::step_prepare_kernel<kNt, kEpt><<<1, L.threads, L.smem, st>>>(
+            cur_p, dst_p, n, (grsr::StepState *)dstate, (int32_t *)dcands, cap)));
+        GRSR_DISPATCH_SHAPE(L.threads, L.ept, (grsr::trial_batch_kernel<kNt, kEpt><<<LT.grid, LT.threads, LT.smem, st>>>(
+            cur_p, dst_p, n, (const int32_t *)dcands, 0LL, (int32_t *)dd2, ncand_dev)));
+        grsr::step_select_kernel<<<1, 256, 0, st>>>(cur_p, n, (grsr::StepState *)dstate,
+                                                    (const int32_t *)dcands, (const int32_t *)dd2,
+                                                    steps_p, max_steps);
+      }
       CK(cudaGetLastError());
       CK(cudaMemcpyAsync(&hs, dstate, sizeof hs, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));

@@ -30,7 +30,11 @@ struct StepState {
   unsigned long long lastkey;      // every candidate with key <= lastkey of this step has been rejected
   unsigned long long batch_end;    // largest key of the current batch
   unsigned long long evals;        // full trial evaluations made so far (whole batches are scored)
+  int32_t target;                  // candidates wanted in the next batch of a hurdle step (0: kStepFirstBatch)
+  int32_t failed;                  // candidates scored without success in the earlier batches of this step
 };
+
+static const int kStepFirstBatch = 256;   // first batch of a hurdle step; x4 after every batch without success
 
 // One block.  cur/dst: the pair (global, int32).  cands: capacity cap pairs (i, j).
 template <int NT, int EPT>
@@ -119,9 +123,17 @@ step_prepare_kernel(const int32_t *__restrict__ cur, const int32_t *__restrict__
     }
   } else {
     // hurdles: every pair of breakpoint edges (e1 < e2) is a candidate (i = e1, j = e2 - 1), key
-    // (e2 - e1 - 1, e1).  Whole diagonals are appended, smallest first, until the batch holds
-    // >= cap / 2 candidates (a diagonal has at most n + 1 <= cap / 2 entries); empty diagonals are
-    // skipped by a block-wide minimum of every edge's next gap.
+    // (e2 - e1 - 1, e1).  Diagonals are appended in key order, smallest first, until the batch holds
+    // about `target` candidates; a diagonal that does not fit is cut after its first entries in e1 order
+    // (ordered compaction), so a batch is always "every candidate with key in (lastkey, batch_end]".
+    // target starts small -- the first success is usually among the first candidates, and scoring a
+    // whole diagonal of n entries for it wastes thousands of evaluations -- and is quadrupled by
+    // step_select_kernel after a batch without success.  Empty diagonals are skipped by a block-wide
+    // minimum of every edge's next gap.
+    int target = st->target;
+    if (target < 1) target = kStepFirstBatch;
+    if (target > cap) target = cap;
+    uint16_t *LST = wk.A1;                           // free once G0 is built: one diagonal's e1 list
     int g = (lastkey == kNoKey) ? 0 : g_last;        // diagonal to resume in
     bool partial = (lastkey != kNoKey);              // first diagonal: only entries with e1 > i_last
     for (;;) {
@@ -138,27 +150,29 @@ step_prepare_kernel(const int32_t *__restrict__ cur, const int32_t *__restrict__
       if (mg == kNoKey) break;                       // no candidate left at all
       const bool resumed = partial && ((int)mg == g);
       g = (int)mg;
-      // append diagonal g (unordered inside the batch: the selection takes the smallest key)
-      if (tid == 0) *shared_u = (unsigned)ncand;
-      __syncthreads();
-      for (int t = tid; t < nbp; t += NT) {
+      // the entries of diagonal g (after i_last if it is the resumed one), ascending e1
+      const int cnt = blk_compact(nbp, [&](int t, unsigned &val) -> bool {
         const int e1 = (int)BPL[t];
-        if (resumed && e1 <= i_last) continue;
+        if (resumed && e1 <= i_last) return false;
         const int want = e1 + 1 + g;
         int lo = t + 1, hi = nbp;
         while (lo < hi) { int mid = (lo + hi) >> 1; if ((int)BPL[mid] < want) lo = mid + 1; else hi = mid; }
-        if (lo < nbp && (int)BPL[lo] == want) {
-          const unsigned slot = atomicAdd((unsigned *)&wk.red[33], 1u);
-          cands[2 * slot] = e1; cands[2 * slot + 1] = want - 1;
-        }
+        if (lo >= nbp || (int)BPL[lo] != want) return false;
+        val = (unsigned)e1; return true;
+      }, LST, wk.red);
+      const int room = min(target, cap) - ncand;
+      const int take = cnt < room ? cnt : room;
+      for (int q = tid; q < take; q += NT) {
+        const int e1 = (int)LST[q];
+        cands[2 * (ncand + q)] = e1; cands[2 * (ncand + q) + 1] = e1 + g;
       }
-      __syncthreads();
-      ncand = (int)*shared_u;
-      batch_end = ((unsigned long long)(unsigned)g << 32) | 0xFFFFFFFFull;   // the whole diagonal is in
+      ncand += take;
+      batch_end = (take == cnt) ? (((unsigned long long)(unsigned)g << 32) | 0xFFFFFFFFull)   // the whole diagonal is in
+                                : (((unsigned long long)(unsigned)g << 32) | (unsigned)LST[take - 1]);
       __syncthreads();
       partial = false;
       g++;
-      if (ncand >= cap / 2 || g > n) break;
+      if (ncand >= target || ncand >= cap || g > n) break;
     }
   }
   if (tid == 0) {
@@ -190,11 +204,23 @@ step_select_kernel(int32_t *cur, int n, StepState *st, const int32_t *__restrict
       st->found = 0;
       if (ncand == 0) st->status = GRSR_SCEN_STUCK;          // nothing left to try
       st->lastkey = st->batch_end;
+      st->failed += ncand;
+      const int t0 = st->target < 1 ? kStepFirstBatch : st->target;
+      st->target = t0 < (1 << 24) ? 4 * t0 : t0;             // nothing in this batch: a bigger one next
     }
     return;
   }
   const int fi = (int)(best & 0xFFFFFFFFull), fj = fi + (int)(best >> 32);
   if (st->nsteps >= max_steps) { if (tid == 0) { st->status = GRSR_SCEN_OVERFLOW; st->found = 0; } return; }
+  // how many candidates the reference's sequential scan would have scored for this step: those of the
+  // failed batches plus the ones of this batch up to the winner.  The next step starts with a batch of
+  // one and a half times that (consecutive steps of a hurdle-rich scenario need similar numbers).
+  unsigned long long upto = 0;
+  for (int c = tid; c < ncand; c += blockDim.x) {
+    const unsigned i = (unsigned)cands[2 * c], j = (unsigned)cands[2 * c + 1];
+    upto += ((((unsigned long long)(j - i) << 32) | i) <= best) ? 1ull : 0ull;
+  }
+  upto = blk_sum_u64(upto, red);
   for (int k = tid; 2 * k <= fj - fi; k += blockDim.x) {
     const int a = fi + k, b = fj - k;
     const int32_t x = cur[a], y = cur[b];
@@ -205,6 +231,10 @@ step_select_kernel(int32_t *cur, int n, StepState *st, const int32_t *__restrict
     st->nsteps = st->nsteps + 1;
     st->found = 1;
     st->lastkey = ~0ull;
+    const long long needed = (long long)st->failed + (long long)upto;
+    const long long next = needed + needed / 2;
+    st->target = (int32_t)(next < kStepFirstBatch ? kStepFirstBatch : (next > (1 << 24) ? (1 << 24) : next));
+    st->failed = 0;
   }
 }
 

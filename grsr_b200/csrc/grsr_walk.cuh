@@ -50,7 +50,7 @@ namespace grsr {
 static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a walk (or an adjacency end)
 static const int kWalkMaxNodes = 256;        // nodes (possible walk starts) per pair
 static const int kWalkMaxWalks = 128;        // walks per pair (4 words per lane in the jumping phase; ids fit a byte)
-static const int kWalkGroup = 8;             // tau steps between two votes
+static const int kWalkGroup = 12;            // tau steps between two votes (same-box A/B: 6 / 8 / 12 / 16 / 24 -> 4.68 / 4.64 / 4.59 / 4.60 / 4.69 ms)
 static const int kWalkIdle = 8;              // default: lanes that must be out of work before new walks start
 static const int kWalkGuide4 = 6;            // guided self-scheduling: a claim takes remaining / (kWalkGuide4 / 4 x takers)
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
