@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -396,9 +397,9 @@ int validate_and_invert(int32_t *d_genomes, int G, int n, int32_t *d_sinv, unsig
   return GRSR_OK;
 }
 
-int validation_error(unsigned long long err, const int32_t *genomes_host, int n) {
+int validation_error(unsigned long long err, const int32_t *genomes_host, int n, long long row0 = 0) {
   if (err == ~0ull) return GRSR_OK;
-  long long row = (long long)(err >> 34);
+  long long row = row0 + (long long)(err >> 34);
   int pos = (int)((err >> 2) & 0xFFFFFFFFull), kind = (int)(err & 3ull);
   long long g = genomes_host[row * n + pos], a = g < 0 ? -g : g;
   if (kind == 0) return fail(GRSR_ERR_INVALID, "genome %lld: input gene == 0", row + 1);
@@ -614,6 +615,96 @@ int shard_pairs(const int32_t *genomes, int G, int n, PairSource src, const int3
   });
 }
 
+// (Optional, GRSR_GATHER=1.)  The table of a multi-device matrix call, the NVLink way: device d uploads, validates and inverts only
+// ITS 1/N of the genome rows (one PCIe copy of the table in total instead of N), records an event, and
+// every device then pulls the other slices -- genomes and signed inverses -- from their owners with peer
+// copies.  State shared by the N host threads of one call.
+struct TableGather {
+  int ngpus = 0;
+  void *dg[kMaxDevices] = {}, *ds[kMaxDevices] = {};
+  cudaEvent_t ready[kMaxDevices] = {};
+  std::atomic<int> arrived{0};
+  std::atomic<int> failed{0};
+};
+cudaEvent_t g_gather_event[kMaxDevices] = {};
+
+// One device's share of a matrix call with a gathered table (matrix mode only: results are scattered into
+// d_matrix by the kernels).
+int run_matrix_slice_gathered(TableGather &T, int d, int first_device, const int32_t *genomes, int G, int n,
+                              long long first, long long count, int32_t *d_matrix) {
+  const int dev = first_device + d, N = T.ngpus;
+  auto arrive = [&](bool ok) {                          // every thread passes here exactly once, error or not
+    if (!ok) T.failed.store(1);
+    T.arrived.fetch_add(1);
+    while (T.arrived.load() < N) std::this_thread::yield();
+  };
+  if (dev < 0 || dev >= kMaxDevices) { arrive(false); return fail(GRSR_ERR_NODEVICE, "device %d out of range", dev); }
+  cudaError_t e0 = cudaSetDevice(dev);
+  DevCache &c = g_cache[dev];
+  std::lock_guard<std::recursive_mutex> lk(c.mu);
+  const size_t gbytes = (size_t)G * n * sizeof(int32_t);
+  void *dg = nullptr, *ds = nullptr, *dp = nullptr, *derr = nullptr;
+  int rc = GRSR_OK;
+  const long long r0 = (long long)G * d / N, r1 = (long long)G * (d + 1) / N;
+  bool ok = (e0 == cudaSuccess);
+  if (ok && !c.stream) ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess;
+  if (ok && !g_gather_event[dev]) ok = cudaEventCreateWithFlags(&g_gather_event[dev], cudaEventDisableTiming) == cudaSuccess;
+  cudaStream_t st = c.stream;
+  if (ok) {
+    rc = cache_reserve(c, 0, gbytes, &dg);
+    if (!rc) rc = cache_reserve(c, 1, gbytes, &ds);
+    if (!rc) rc = cache_reserve(c, 2, (size_t)(count > 0 ? count : 1) * 2 * sizeof(int32_t), &dp);
+    if (!rc) rc = cache_reserve(c, 6, sizeof(unsigned long long), &derr);
+    ok = (rc == GRSR_OK);
+  }
+  if (ok) {
+    for (int q = 0; q < N; q++) peer_ok(dev, first_device + q);
+    T.dg[d] = dg; T.ds[d] = ds; T.ready[d] = g_gather_event[dev];
+    if (count > 0) ok = grsr_triangle_pairs_dev(G, first, count, (int32_t *)dp, st) == GRSR_OK;
+    const size_t off = (size_t)r0 * n, sl = (size_t)(r1 - r0) * n;
+    ok = ok && cudaMemcpyAsync((int32_t *)dg + off, genomes + off, sl * sizeof(int32_t), cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok && r1 > r0)
+      ok = validate_and_invert((int32_t *)dg + off, (int)(r1 - r0), n, (int32_t *)ds + off, (unsigned long long *)derr, st) == GRSR_OK;
+    else if (ok)
+      ok = cudaMemsetAsync(derr, 0xff, sizeof(unsigned long long), st) == cudaSuccess;
+    ok = ok && cudaEventRecord(T.ready[d], st) == cudaSuccess;
+  }
+  arrive(ok);                                           // all slices are on their way (or somebody failed)
+  if (!ok || T.failed.load()) {
+    if (e0 == cudaSuccess && c.stream) cudaStreamSynchronize(c.stream);
+    if (ok) return GRSR_OK;                             // another device reports the error
+    if (rc) return rc;
+    cudaError_t e = cudaGetLastError();
+    return fail(GRSR_ERR_CUDA, "table upload failed on device %d: %s", dev, cudaGetErrorString(e != cudaSuccess ? e : e0));
+  }
+  unsigned long long err = ~0ull;
+  const int rcb = [&]() -> int {
+    for (int q = 0; q < N; q++) {                        // pull the other slices from their owners over NVLink
+      if (q == d) continue;
+      const long long q0 = (long long)G * q / N, q1 = (long long)G * (q + 1) / N;
+      if (q1 <= q0) continue;
+      const size_t off = (size_t)q0 * n, bytes = (size_t)(q1 - q0) * n * sizeof(int32_t);
+      CK(cudaStreamWaitEvent(st, T.ready[q], 0));
+      CK(cudaMemcpyPeerAsync((int32_t *)dg + off, dev, (int32_t *)T.dg[q] + off, first_device + q, bytes, st));
+      CK(cudaMemcpyPeerAsync((int32_t *)ds + off, dev, (int32_t *)T.ds[q] + off, first_device + q, bytes, st));
+    }
+    if (count > 0) {
+      int r = dist_pairs_dev_impl((const int32_t *)dg, (const int32_t *)ds, n, (const int32_t *)dp, count, d_matrix,
+                                  -G, st, 1);
+      if (r) return r;
+    }
+    CK(cudaMemcpyAsync(&err, derr, sizeof err, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GRSR_OK;
+  }();
+  if (rcb) cudaStreamSynchronize(st);
+  // nobody may reuse or free a slice while a peer still copies from it: leave together
+  T.arrived.fetch_add(1);
+  while (T.arrived.load() < 2 * N) std::this_thread::yield();
+  if (rcb) return rcb;
+  return validation_error(err, genomes, n, r0);          // the error word counts rows from the slice's first
+}
+
 // setinvmatrix on ngpus devices.  The G x G matrix lives on the first device; every device's kernels
 // store their distances straight into it, both [i][j] and [j][i] (the other devices through NVLink
 // peer mappings, 8 bytes per pair), the first device zeroes the diagonal, and ONE device-to-host copy
@@ -644,11 +735,23 @@ int matrix_on_devices(const int32_t *genomes, int G, int n, int32_t *distmatrix,
   int rc = cache_reserve(c, 8, (size_t)G * G * sizeof(int32_t), &dmat);
   if (rc) return rc;
   CK(cudaMemset2DAsync(dmat, (size_t)(G + 1) * sizeof(int32_t), 0, sizeof(int32_t), (size_t)G, c.stream));
-  rc = on_devices(first_device, ngpus, [&](int d) {
-    long long lo = P * d / ngpus, hi = P * (d + 1) / ngpus;
-    return run_pairs_on_device(first_device + d, genomes, G, n, PAIRS_TRIANGLE, nullptr, lo, hi - lo,
-                               nullptr, -G, (int32_t *)dmat);
-  });
+  // Measured at N = 8 on config 3 (gpurun_out/r2w_bench_n8*.json): 1.283 ms per call with the gathered
+  // table against 1.228 ms with eight full uploads -- the 14 peer copies and the host rendezvous cost
+  // more than the PCIe time they save (the eight links run in parallel).  Kept as an option, off by default.
+  if (ngpus > 1 && G >= ngpus && env_int("GRSR_GATHER", 0)) {
+    TableGather T;
+    T.ngpus = ngpus;
+    rc = on_devices(first_device, ngpus, [&](int d) {
+      long long lo = P * d / ngpus, hi = P * (d + 1) / ngpus;
+      return run_matrix_slice_gathered(T, d, first_device, genomes, G, n, lo, hi - lo, (int32_t *)dmat);
+    });
+  } else {
+    rc = on_devices(first_device, ngpus, [&](int d) {
+      long long lo = P * d / ngpus, hi = P * (d + 1) / ngpus;
+      return run_pairs_on_device(first_device + d, genomes, G, n, PAIRS_TRIANGLE, nullptr, lo, hi - lo,
+                                 nullptr, -G, (int32_t *)dmat);
+    });
+  }
   if (rc) return rc;
   CK(cudaSetDevice(first_device));
   CK(cudaMemcpyAsync(distmatrix, dmat, (size_t)G * G * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));

@@ -102,6 +102,30 @@ def test_caller_device_is_left_alone():
 
 
 @pytest.mark.skipif("_ndev() < 2")
+def test_multi_gpu_matrix_table_gather_and_errors():
+    """ngpus > 1, both table paths: every device uploads the whole table (default), or (GRSR_GATHER=1)
+    every device uploads and validates 1/N of the rows and the rest arrives by NVLink peer copies.  Same
+    matrix; an offence in any slice is reported with its global genome number."""
+    g = U.mixed_genomes(120, 75, seed=8)
+    want = _matrix_from_oracle(g)
+    for gather in ("0", "1"):
+        os.environ["GRSR_GATHER"] = gather
+        try:
+            for k in range(2, _ndev() + 1):
+                assert np.array_equal(capi.dist_matrix(g, ngpus=k), want), (gather, k)
+            for row in (0, 37, 74):                         # first, middle and last slice
+                bad = g.copy()
+                bad[row, 3] = bad[row, 4]
+                with pytest.raises(capi.GrsrError, match="genome %d: duplicate gene" % (row + 1)):
+                    capi.dist_matrix(bad, ngpus=_ndev())
+            assert np.array_equal(capi.dist_matrix(g, ngpus=_ndev()), want)      # and the next call is fine
+            small = U.mixed_genomes(40, 3, seed=2)          # fewer genomes than devices on an 8-GPU box
+            assert np.array_equal(capi.dist_matrix(small, ngpus=_ndev()), _matrix_from_oracle(small))
+        finally:
+            os.environ.pop("GRSR_GATHER", None)
+
+
+@pytest.mark.skipif("_ndev() < 2")
 @pytest.mark.parametrize("no_peer", [0, 1])
 def test_multi_gpu_matrix_and_stats(no_peer):
     os.environ["GRSR_NO_PEER"] = str(no_peer)
