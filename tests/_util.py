@@ -147,6 +147,7 @@ def emulator():
         from grsr_b200 import build
         build.build_emu()
         _emu = ctypes.CDLL(os.path.join(ROOT, "tests", "emu", "libgrsr_emu.so"))
+        _emu.emu_last_stepwise_evals.restype = ctypes.c_longlong
     return _emu
 
 

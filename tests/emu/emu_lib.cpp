@@ -111,6 +111,9 @@ extern "C" int emu_trial_distances(const int32_t *src, const int32_t *dst, int n
 
 // candidate-parallel steps while hurdles exist, then the persistent kernel for the rest -- the same
 // host loop as scenario_on_device() in grsr_capi.cu, with every launch going through the emulator
+static long long g_stepwise_evals = 0;   // candidates scored by the candidate-parallel phase of the last call
+extern "C" long long emu_last_stepwise_evals() { return g_stepwise_evals; }
+
 extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int npairs, int n,
                                      int32_t *steps, int32_t *nsteps, int max_steps, int32_t *status,
                                      int threads, int cap, int *stepwise_steps) {
@@ -121,6 +124,7 @@ extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int
   std::vector<int32_t> cur((size_t)npairs * n), cands((size_t)cap * 2), d2((size_t)cap);
   memcpy(cur.data(), src, sizeof(int32_t) * (size_t)npairs * n);
   *stepwise_steps = 0;
+  g_stepwise_evals = 0;
   for (int p = 0; p < npairs; p++) {
     grsr::StepState st;
     memset(&st, 0, sizeof st);
@@ -143,6 +147,7 @@ extern "C" int emu_scenario_stepwise(const int32_t *src, const int32_t *dst, int
     }
     nsteps[p] = st.nsteps; status[p] = st.status;
     *stepwise_steps += st.nsteps;
+    g_stepwise_evals += (long long)st.evals;
   }
   unsigned int ticket = 0;
   size_t smem = smem_prep;

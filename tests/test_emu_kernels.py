@@ -125,12 +125,19 @@ def test_emulated_stepwise_scenarios():
                 src, dst = gen.random_signed_perm(n, rng), gen.hurdle_rich_perm(n, seed)
             srcs.append(src)
             dsts.append(dst)
-        for cap in (0, 2 * (n + 1)):
+        wants = [U.orc_scenario(s, d) for s, d in zip(srcs, dsts)]
+        ref_evals = sum(w[1] for w in wants)
+        ref_steps = sum(len(w[0]) for w in wants)
+        for cap in (0, 2 * (n + 1), 8, 3):              # 8 and 3: batches end inside diagonals, many per step
             steps, status, stepwise_steps = U.emu_scenario_stepwise(srcs, dsts, 0, cap)
             for q in range(len(srcs)):
-                want, _ = U.orc_scenario(srcs[q], dsts[q])
-                assert status[q] == 0 and np.array_equal(steps[q], want)
+                assert status[q] == 0 and np.array_equal(steps[q], wants[q][0])
             assert n < 5 or stepwise_steps > 0
+            # no candidate is scored twice within a step: the candidate-parallel phase scores at most what
+            # the reference's sequential scan scores, plus less than one batch per step
+            scored = U.emulator().emu_last_stepwise_evals()
+            if cap in (3, 8):
+                assert scored <= ref_evals + cap * ref_steps, (n, cap, scored, ref_evals, ref_steps)
 
 
 # ---- the two-tier distance path: warp-per-pair walk kernel + deferred pairs -------------------------
