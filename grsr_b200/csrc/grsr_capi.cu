@@ -542,7 +542,7 @@ int run_pairs_on_device(int dev, const int32_t *genomes, int G, int n, PairSourc
 // one after the other, which is a quarter of a millisecond before the last device even starts -- as much
 // as a third of the kernel time of an 8-way matrix.  Workers sleep on a condition variable between calls.
 struct WorkerPool {
-  std::mutex call_mu;                 // one multi-device call at a time
+  std::recursive_mutex call_mu;       // one multi-device call at a time; taken BEFORE any per-device lock
   std::mutex mu;
   std::condition_variable cv_go, cv_done;
   std::vector<std::thread> threads;
@@ -588,7 +588,7 @@ int on_devices(int first_device, int ngpus, F work) {
   std::vector<std::string> errs(ngpus);
   if (ngpus > 1) {
     WorkerPool &pool = worker_pool();
-    std::lock_guard<std::mutex> one_call(pool.call_mu);
+    std::lock_guard<std::recursive_mutex> one_call(pool.call_mu);
     pool.start(ngpus - 1, [&](int d) { rcs[d] = work(d); if (rcs[d]) errs[d] = g_err; });
     rcs[0] = work(0);
     if (rcs[0]) errs[0] = g_err;
@@ -727,6 +727,10 @@ int matrix_on_devices(const int32_t *genomes, int G, int n, int32_t *distmatrix,
     }
     return GRSR_OK;
   }
+  // lock order of every multi-device call: the pool, then device caches (the first device's here, the
+  // others' in their worker threads)
+  std::unique_lock<std::recursive_mutex> pool_lock(worker_pool().call_mu, std::defer_lock);
+  if (ngpus > 1) pool_lock.lock();
   CK(cudaSetDevice(first_device));
   DevCache &c = g_cache[first_device];
   std::lock_guard<std::recursive_mutex> lk(c.mu);       // held for the whole call: the matrix is ours
@@ -923,6 +927,8 @@ int scenario_call(const int32_t *src, const int32_t *dst, int npairs, int n, grs
   int rc = check_genes_fit(n);
   if (rc) return rc;
   std::lock_guard<std::mutex> arena_lock(g_arena.mu);
+  std::unique_lock<std::recursive_mutex> pool_lock(worker_pool().call_mu, std::defer_lock);
+  if (ngpus > 1) pool_lock.lock();                      // before any per-device lock (see matrix_on_devices)
   const size_t ms = (size_t)(max_steps > 0 ? max_steps : 1);
   const size_t sbytes = (((size_t)npairs * ms * 2 * sizeof(int32_t)) + 15) & ~(size_t)15;
   const size_t ibytes = (((size_t)npairs * sizeof(int32_t)) + 15) & ~(size_t)15;

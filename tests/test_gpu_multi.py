@@ -173,3 +173,41 @@ def test_multi_gpu_scenario_queue(no_peer):
             assert all(np.array_equal(a, b[:7]) for a, b in zip(pre, want)), ng
     finally:
         os.environ.pop("GRSR_NO_PEER", None)
+
+
+@pytest.mark.skipif("_ndev() < 2")
+def test_concurrent_multi_device_calls_from_two_host_threads():
+    """Two host threads in multi-device calls at once (matrix and scenarios): the calls serialise on the
+    worker pool, take their per-device locks in one order, and both return the right answers."""
+    import threading
+    g = U.mixed_genomes(90, 60, seed=5)
+    want_m = _matrix_from_oracle(g)
+    rng = random.Random(9)
+    srcs = np.array([gen.random_signed_perm(90, rng) for _ in range(40)], dtype=np.int32)
+    dsts = np.array([gen.hurdle_rich_perm(90, s) for s in range(40)], dtype=np.int32)
+    want_s = [U.orc_scenario(s, d)[0] for s, d in zip(srcs, dsts)]
+    errors = []
+
+    def matrices():
+        try:
+            for _ in range(6):
+                assert np.array_equal(capi.dist_matrix(g, ngpus=_ndev()), want_m)
+                assert np.array_equal(capi.dist_matrix(g, ngpus=1), want_m)
+        except Exception as e:                               # noqa: BLE001
+            errors.append(e)
+
+    def scenarios():
+        try:
+            for _ in range(3):
+                got = capi.scenario_batch(srcs, dsts, ngpus=_ndev())
+                assert all(np.array_equal(a, b) for a, b in zip(got, want_s))
+        except Exception as e:                               # noqa: BLE001
+            errors.append(e)
+
+    ths = [threading.Thread(target=matrices), threading.Thread(target=scenarios), threading.Thread(target=matrices)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=300)
+    assert not any(t.is_alive() for t in ths), "deadlock between concurrent multi-device calls"
+    assert not errors, errors
