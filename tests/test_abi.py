@@ -35,7 +35,8 @@ def test_no_cpu_fallback_without_device():
     g = np.array([[1, 2, 3], [3, -2, 1]], dtype=np.int32)
     for call in (lambda: capi.dist_matrix(g), lambda: capi.dist_pairs(g, [[0, 1]]),
                  lambda: capi.stats_matrix(g), lambda: capi.scenario_batch(g[0], g[1]),
-                 lambda: capi.dist_matrix_shard(g, 0, 1)):
+                 lambda: capi.dist_matrix_shard(g, 0, 1), lambda: capi.scenario_prefix(g[0], g[1], 2),
+                 lambda: capi.unsigned_dist(g[0], g[1]), lambda: capi.trial_distances(g[0], g[1], [[0, 1]])):
         with pytest.raises(capi.GrsrError) as e:
             call()
         assert e.value.code == capi.ERR_NODEVICE
