@@ -69,6 +69,16 @@ def build_cuda_profile(force: bool = False, tag: str = "", defines: tuple = ()) 
     return out
 
 
+def build_cuda_variant(tag: str, defines: tuple = (), force: bool = False) -> str:
+    """Experimental twin of the library (lib/libgrsr_cuda<tag>.so) for same-box A/B runs: select it with
+    GRSR_LIB=<path> (grsr_b200/capi.py), e.g. tag="_g8", defines=("-DGRSR_WALK_GROUP=8",)."""
+    out = os.path.join(LIBDIR, "libgrsr_cuda%s.so" % tag)
+    os.makedirs(LIBDIR, exist_ok=True)
+    if force or not _newer(out, cuda_sources()):
+        _run([_nvcc(), *NVCC_FLAGS, *defines, "-o", out, os.path.join(CSRC, "grsr_capi.cu")])
+    return out
+
+
 def cli_sources() -> list[str]:
     return [os.path.join(CSRC, f) for f in ("grimm_main.c",)] + [os.path.join(ROOT, "include", "grsr.h")]
 

@@ -50,7 +50,10 @@ namespace grsr {
 static const unsigned kVis = 0x8000u;        // H entry: vertex claimed by a walk (or an adjacency end)
 static const int kWalkMaxNodes = 256;        // nodes (possible walk starts) per pair
 static const int kWalkMaxWalks = 128;        // walks per pair (4 words per lane in the jumping phase; ids fit a byte)
-static const int kWalkGroup = 12;            // tau steps between two votes (same-box A/B: 6 / 8 / 12 / 16 / 24 -> 4.68 / 4.64 / 4.59 / 4.60 / 4.69 ms)
+#ifndef GRSR_WALK_GROUP
+#define GRSR_WALK_GROUP 12
+#endif
+static const int kWalkGroup = GRSR_WALK_GROUP;          // tau steps between two votes (same-box A/B: 6 / 8 / 12 / 16 / 24 -> 4.68 / 4.64 / 4.59 / 4.60 / 4.69 ms)
 static const int kWalkIdle = 8;              // default: lanes that must be out of work before new walks start
 static const int kWalkGuide4 = 6;            // guided self-scheduling: a claim takes remaining / (kWalkGuide4 / 4 x takers)
 static const int kWalkMaxUnoriented = 30;    // unoriented cycles probed per pair before deferring
@@ -63,6 +66,21 @@ __host__ __device__ inline int walk_shift(int n) {
   while (((S + (1 << sh) - 1) >> sh) > kWalkMaxNodes) sh++;
   return sh;
 }
+
+// Node k sits at vertex (k << shift) + skew(k), skew even and below the stride, chosen so that the H
+// entries of any 32 consecutive nodes lie in 32 different shared-memory banks (the warp examines 32
+// nodes per load; on the plain grid they would share 32 / 2^(shift-1) banks).  Entry of vertex x: 16-bit
+// index x + 1, i.e. word x / 2 for even x; node stride = 2^(shift-1) words.
+struct WalkGrid {
+  int shift, s1;
+  unsigned m1;
+  __device__ inline explicit WalkGrid(int sh) : shift(sh), s1(sh < 6 ? 6 - sh : 0) {
+    const unsigned words = 1u << (sh - 1);
+    m1 = (words < 32u ? words : 32u) - 1u;
+  }
+  __device__ inline unsigned vertex(unsigned k) const { return (k << shift) + 2u * ((k >> s1) & m1); }
+  __device__ inline bool is_node(unsigned x) const { return x == vertex(x >> shift); }
+};
 
 // kernel argument: node stride and start threshold in one int
 __host__ __device__ inline int walk_shape_arg(int shift, int idle_min) { return shift | (idle_min << 8); }
@@ -81,11 +99,11 @@ __host__ __device__ inline size_t walk_warp_bytes(int n) { return walk_tail_byte
 // cycle owns an oriented grey edge: walk to the next start of a walk and read its converged word,
 // or get round an orbit that has none.
 __device__ inline unsigned walk_cycle_of(const uint16_t *H, const uint32_t *NW, const uint8_t *MAP,
-                                         unsigned v, unsigned mask, int shift, unsigned &oriented) {
+                                         unsigned v, const WalkGrid &grid, unsigned &oriented) {
   unsigned x = v, mn = v, orr = 0;
   for (;;) {
-    if ((x & mask) == 0u) {
-      const unsigned id = MAP[x >> shift];
+    if (!(x & 1u) && grid.is_node(x)) {
+      const unsigned id = MAP[x >> grid.shift];
       if (id != 0xFFu) {
         const uint32_t w = NW[id];
         oriented = ((orr & 1u) | ((w >> 1) & 1u));
@@ -100,20 +118,50 @@ __device__ inline unsigned walk_cycle_of(const uint16_t *H, const uint32_t *NW, 
   }
 }
 
-// Ends of gamma's gene g in pi (vertices): tail[a-1] = where gene +a begins.  Positions past the
-// last gene hold the sentinel gene n+1, whose tail entry is the frame vertex 2n+1 (its "left end").
+// Ends of gamma's gene g in pi (vertices): tail[a-1] = where gene +a begins, MINUS ONE (2p if pi holds
+// +a at position p, else 2p+1), so that the sign of g is one XOR away.  Positions past the last gene
+// hold the sentinel gene n+1, whose tail entry is the frame vertex 2n+1 (its "left end").
 __device__ inline void walk_ends(const uint16_t *tail, int g, unsigned &L, unsigned &R) {
-  const unsigned v = tail[(g > 0 ? g : -g) - 1];
-  const unsigned h = ((v - 1u) ^ 1u) + 1u;
-  L = (g > 0) ? v : h;
-  R = (g > 0) ? h : v;
+  const unsigned t = (unsigned)tail[(g > 0 ? g : -g) - 1] ^ ((unsigned)g >> 31);
+  L = t + 1u;
+  R = (t ^ 1u) + 1u;
 }
+// the staged form of one entry of the signed inverse row
+__device__ inline uint16_t walk_tail_entry(int s) { return (uint16_t)(s > 0 ? 2 * s - 2 : -2 * s - 1); }
 
 // (hi16 << 16) | lo16 of two 16-bit values
 #ifdef GRSR_EMU
 __device__ inline unsigned walk_pack(unsigned lo16, unsigned hi16) { return (lo16 & 0xFFFFu) | (hi16 << 16); }
+__device__ inline unsigned walk_rotl(unsigned w, unsigned by) { by &= 31u; return by ? (w << by) | (w >> (32u - by)) : w; }
 #else
 __device__ inline unsigned walk_pack(unsigned lo16, unsigned hi16) { return __byte_perm(lo16, hi16, 0x5410); }
+__device__ inline unsigned walk_rotl(unsigned w, unsigned by) { return __funnelshift_l(w, w, by); }   // by mod 32
+#endif
+
+// The tau steps carry the shared-memory ADDRESS of the entry under examination instead of the vertex:
+// the claim goes to the address the entry was loaded from, the next address is one add away, and both
+// the segment minimum (addresses grow with the vertex) and the orientation parity (bit 1 of the address
+// = bit 0 of the vertex, H being 4-byte aligned) can be kept on addresses.
+#ifdef GRSR_EMU
+typedef uintptr_t walk_addr_t;
+__device__ inline walk_addr_t walk_addr_of(const void *p) { return (uintptr_t)p; }
+__device__ inline unsigned walk_lds16(walk_addr_t a) { return *(const uint16_t *)a; }
+__device__ inline void walk_sts16(walk_addr_t a, unsigned v) { *(uint16_t *)a = (uint16_t)v; }
+__device__ inline void walk_sts32(walk_addr_t a, unsigned v) { *(uint32_t *)a = v; }
+#else
+typedef unsigned walk_addr_t;
+__device__ inline walk_addr_t walk_addr_of(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ inline unsigned walk_lds16(walk_addr_t a) {
+  unsigned v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ inline void walk_sts16(walk_addr_t a, unsigned v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ inline void walk_sts32(walk_addr_t a, unsigned v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 #endif
 
 // Genes t0 .. t0+7 of a row (n+1 past the end): two 16-byte loads when the row allows it.
@@ -215,8 +263,8 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   uint32_t *Hw = wm.Hw, *NW = wm.NW, *UL = wm.UL;
   uint8_t *MAP = wm.MAP;
   uint16_t *H = (uint16_t *)Hw;
-  const unsigned mask = (1u << shift) - 1u;
-  const int K = (S + (int)mask) >> shift;            // nodes 0 .. K-1 <-> vertices i << shift
+  const WalkGrid grid(shift);
+  const int K = (S + (1 << shift) - 1) >> shift;     // nodes 0 .. K-1 (the last one may fall past the last vertex)
   const bool vec = ((n & 3) == 0) && ((((size_t)genomes) & 15) == 0);
 
   if (lane == 0) UL[0] = 0;
@@ -230,17 +278,17 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
   const int32_t *gamma = genomes + (long long)gi * n;
   unsigned nadj = 0;
   {
+    const walk_addr_t hw1 = walk_addr_of(Hw) + 1u;
     int G[8], Gn[8];
     walk_load8(gamma, 8 * lane, n, vec, G);
     unsigned carry = 0;                               // right end of the gene before this chunk (vertex 0 first)
     for (int cb = 0; cb < n; cb += 256) {
       const int tb = cb + 8 * lane;
       walk_load8(gamma, tb + 256, n, vec, Gn);
-      unsigned L[8], R[8], Lx, Rx;
+      unsigned L[8], R[8], Lx = 0, Rx;
 #pragma unroll
       for (int k = 0; k < 8; k++) walk_ends(tail, G[k], L[k], R[k]);
-      walk_ends(tail, Gn[0], Lx, Rx);
-      (void)Rx;
+      if (lane == 0) walk_ends(tail, Gn[0], Lx, Rx);    // the first gene of the next chunk: lane 31's right neighbour
       unsigned pr = __shfl_up_sync(kFull, R[7], 1);
       if (lane == 0) pr = carry;
       const unsigned nl0 = __shfl_sync(kFull, Lx, 0);
@@ -250,18 +298,24 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       // the chunk's genes; a chunk that lies wholly inside the row has no sentinel genes to mask
       auto genes = [&](auto all_real) {
         constexpr bool kAllReal = decltype(all_real)::value;
+        // m[k] = kVis when grey edge (gene k-1, gene k) of this lane's 8 genes is an adjacency: R_{k-1} ^ 1 == L_k
+        unsigned m[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          const unsigned Rp = (k == 0) ? pr : R[(k + 7) & 7], Lk = (k == 8) ? nl : L[k & 7];
+          m[k] = ((Rp ^ Lk ^ 1u) == 0u) ? kVis : 0u;
+        }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           const unsigned Lt = L[k], Rt = R[k];
-          const unsigned a = ((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u;     // tau(L_t) = R_{t-1} ^ 1
-          const unsigned b = ((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u;     // tau(R_t) = L_{t+1} ^ 1
+          const unsigned ea = (((k == 0) ? pr : R[(k + 7) & 7]) ^ 1u) | m[k];       // tau(L_t) = R_{t-1} ^ 1
+          const unsigned eb = (((k == 7) ? nl : L[(k + 1) & 7]) ^ 1u) | m[k + 1];   // tau(R_t) = L_{t+1} ^ 1
           const bool real = kAllReal || (tb + k < n);
-          const bool adjL = (a == Lt), adjR = (b == Rt);                // grey edge t / t+1 is an adjacency
-          nadj += (adjL && real) ? 1u : 0u;
-          const unsigned ea = a | (adjL ? kVis : 0u), eb = b | (adjR ? kVis : 0u);
-          const bool fwd = Lt < Rt;                                     // L_t = 2p+1: its entry is the low half
-          const unsigned word = walk_pack(fwd ? ea : eb, fwd ? eb : ea);
-          if (real) *(uint32_t *)((char *)Hw + Lt + Rt + 1u) = word;    // L_t + R_t + 1 = 4(p+1): word p+1
+          nadj += real ? m[k] : 0u;                                     // in units of kVis
+          // word p+1 = (entry of 2p+1, entry of 2p+2): L_t's entry is the low half iff L_t is odd
+          const unsigned hl = walk_pack(eb, ea);
+          const unsigned word = walk_rotl(hl, Lt << 4);
+          if (real) walk_sts32(hw1 + Lt + Rt, word);                    // L_t + R_t + 1 = 4(p+1): word p+1
         }
       };
       if (cb + 256 <= n) genes(std::true_type()); else genes(std::false_type());
@@ -275,13 +329,14 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       H[1] = (uint16_t)((L0 ^ 1u) | ((L0 == 1u) ? kVis : 0u));         // tau(0) = L_0 ^ 1
       const bool adjn = ((Rl ^ 1u) == (unsigned)S - 1u);
       H[S] = (uint16_t)((Rl ^ 1u) | (adjn ? kVis : 0u));              // tau(2n+1) = R_{n-1} ^ 1
-      nadj += adjn ? 1u : 0u;
+      nadj += adjn ? kVis : 0u;
     }
   }
   __syncwarp();
 
   // ---- walks -------------------------------------------------------------------------------------
-  // A lane without a walk points at the pad entry H[0] (x = nx = -1): a step from there, like a
+  // Lane state: `at` = address of the entry under examination (the vertex the walk steps to next), e =
+  // that entry.  A lane without a walk looks at the pad entry H[0] (claimed): a step from there, like a
   // step of a walk that has ended, changes nothing, so the steps need no "am I walking" test.
   int W = 0;                                          // walks started so far (warp-uniform)
   {
@@ -289,21 +344,25 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     // examined per shared-memory load, the r-th lane out of work takes the r-th free one.
     int pc = 0, myid = -1;                            // pc: first node not examined yet (warp-uniform)
     bool ended = true;
-    unsigned x = 0xFFFFFFFFu, nx = 0xFFFFFFFFu, mn = 0, orr = 0, e = kVis;
+    const walk_addr_t h0 = walk_addr_of(H), h1 = h0 + 2u;   // entry of vertex u: h1 + 2u
+    walk_addr_t at = h0, mn = 0, org = 0, orr = 0;    // org: the walk's first vertex; orr: OR of (vertex ^ first vertex)
+    unsigned e = kVis;
     uint32_t *SCR = UL;                               // 32 words of scratch (UL is not in use yet)
     for (;;) {
       // start section: close the walks that have ended, hand free nodes to the lanes out of work
       if (ended && myid >= 0) {
-        NW[myid] = GRSR_W_MAKE(mn, MAP[nx >> shift], (orr & 1u) ? GRSR_W_ORBIT : 0u);
+        const unsigned hit = (unsigned)((at - h0) >> 1) - 1u;          // the claimed vertex the walk ran into
+        NW[myid] = GRSR_W_MAKE((unsigned)((mn - h0) >> 1) - 1u, MAP[hit >> shift], (orr & 2u) ? GRSR_W_ORBIT : 0u);
         myid = -1;
-        x = 0xFFFFFFFFu; nx = 0xFFFFFFFFu; orr = 0;
+        at = h0;
       }
       const unsigned needm = __ballot_sync(kFull, ended);
       const int myrank = __popc(needm & lt_mask);
       int need = min(__popc(needm), kWalkMaxWalks - W), served = 0;
       while (need > served && pc < K) {
         const int node = pc + lane;
-        const unsigned en = (node < K) ? (unsigned)H[((unsigned)node << shift) + 1] : kVis;
+        const unsigned xn = grid.vertex((unsigned)node);
+        const unsigned en = (node < K && xn < (unsigned)S) ? (unsigned)H[xn + 1] : kVis;
         const bool isfree = !(en & kVis);
         const unsigned fm = __ballot_sync(kFull, isfree);
         const int nf = __popc(fm);
@@ -316,12 +375,14 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
           if (ended && slot >= 0 && slot < take) {
             const unsigned v = SCR[slot];
             const int mynode = pc + (int)(v >> 16);
-            e = v & 0xFFFFu;
+            const unsigned x = grid.vertex((unsigned)mynode), e0 = v & 0xFFFFu;
             myid = W + myrank;
-            x = (unsigned)mynode << shift;
-            H[x + 1] = (uint16_t)(e | kVis);
+            H[x + 1] = (uint16_t)(e0 | kVis);
             MAP[mynode] = (uint8_t)myid;
-            nx = e; mn = x; orr = 0; ended = false;
+            mn = org = h1 + 2u * x;
+            at = h1 + 2u * e0;
+            orr = org ^ at;
+            ended = false;
           }
           const int last = (int)(SCR[take - 1] >> 16);  // lane of the last free node handed out
           __syncwarp();
@@ -335,13 +396,17 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       __syncwarp();
       if (!__any_sync(kFull, !ended)) break;
       const bool pool = (pc < K) && (W < kWalkMaxWalks);  // lanes out of work can still be served
+      e = walk_lds16(at);                             // after every start of this section has claimed its node
       for (;;) {
 #pragma unroll
         for (int s = 0; s < kWalkGroup; s++) {
-          const unsigned u = nx;
-          orr |= x ^ u;
-          e = H[u + 1];
-          if (!(e & kVis)) { H[u + 1] = (uint16_t)(e | kVis); mn = min(mn, u); x = u; nx = e; }
+          if (!(e & kVis)) {                            // unclaimed: claim it (even vertices only) and examine tau of it
+            if (at & 2u) walk_sts16(at, e | kVis);
+            mn = at < mn ? at : mn;
+            at = h1 + 2u * e;
+            orr |= at ^ org;
+            e = walk_lds16(at);
+          }
         }
         ended = (e & kVis) != 0u;
         const unsigned walking = __ballot_sync(kFull, !ended);
@@ -367,14 +432,14 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
     int budget = kWalkLeftoverBudget;
     for (int q = lane; q < hq; q += 32) {                // hq is a multiple of 32: whole rounds
       const uint4 x = H4[q];
-      const bool some = ((x.x & x.y & x.z & x.w) & 0x80008000u) != 0x80008000u;
+      const bool some = ((x.x & x.y & x.z & x.w) & 0x80000000u) == 0u;   // an even vertex (high halves) unclaimed
       if (__any_sync(kFull, some)) {
         if (some) {
-          // bit k of um <-> entry 8q+k unclaimed
-          const unsigned y0 = ~x.x & 0x80008000u, y1 = ~x.y & 0x80008000u;
-          const unsigned y2 = ~x.z & 0x80008000u, y3 = ~x.w & 0x80008000u;
-          unsigned um = ((y0 >> 15) & 1u) | ((y0 >> 30) & 2u) | ((y1 >> 13) & 4u) | ((y1 >> 28) & 8u) |
-                        ((y2 >> 11) & 16u) | ((y2 >> 26) & 32u) | ((y3 >> 9) & 64u) | ((y3 >> 24) & 128u);
+          // bit k of um <-> entry 8q+k (vertex 8q+k-1) unclaimed.  Only EVEN vertices are tried: the
+          // orbit of a cycle's leftmost vertex has an even minimum, its twin an odd one that counts nothing.
+          const unsigned y0 = ~x.x & 0x80000000u, y1 = ~x.y & 0x80000000u;
+          const unsigned y2 = ~x.z & 0x80000000u, y3 = ~x.w & 0x80000000u;
+          unsigned um = (y0 >> 30) | (y1 >> 28) | (y2 >> 26) | (y3 >> 24);
           while (um) {
             const int k = __ffs((int)um) - 1;
             um &= um - 1u;
@@ -388,7 +453,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
               orr |= x1 ^ nx;
               x1 = nx;
             }
-            if (root && !(u0 & 1u)) {
+            if (root) {
               ncyc++;
               if (!(orr & 1u)) {
                 nun++;
@@ -401,7 +466,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       }
     }
   }
-  nadj = __reduce_add_sync(kFull, nadj);
+  nadj = __reduce_add_sync(kFull, nadj) >> 15;        // counted in units of kVis
   ncyc = __reduce_add_sync(kFull, ncyc);
   nun = __reduce_add_sync(kFull, nun);
   defer = __any_sync(kFull, defer);
@@ -428,7 +493,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
           const unsigned ent = H[v + 1];
           if ((ent & 0x7FFFu) != v) {                 // not an adjacency end
             unsigned ori;
-            const unsigned cy = walk_cycle_of(H, NW, MAP, v, mask, shift, ori);
+            const unsigned cy = walk_cycle_of(H, NW, MAP, v, grid, ori);
             if (cy == qq) st = 2;                     // Q's own next vertex: the probe ends here
             else if (cy < qq && ori) st = 1;          // an oriented cycle that starts left of Q
           }
@@ -498,7 +563,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
   wm.tail = tail;
   walk_carve_private(wm, base + walk_tail_bytes(n), n);
   walk_init_private(wm, n, lane);
-  if (lane == 0) tail[n] = (uint16_t)(2 * n + 1);     // the sentinel gene's entry
+  if (lane == 0) tail[n] = (uint16_t)(2 * n);         // the sentinel gene's entry (vertex 2n+1, minus one)
   __syncwarp();
 
   int staged = -1;
@@ -517,7 +582,7 @@ dist_walk_kernel(const int32_t *__restrict__ genomes, const int32_t *__restrict_
         const int32_t *sp = sinv + (long long)pj * n;
         for (int i = lane; i < n; i += 32) {
           const int s = sp[i];
-          tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);   // vertex where gene +(i+1) begins in pi
+          tail[i] = walk_tail_entry(s);                  // vertex where gene +(i+1) begins in pi, minus one
         }
         staged = pj;
         __syncwarp();
@@ -545,7 +610,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
   wm.tail = tail;
   walk_carve_private(wm, smem_raw + 16 + walk_tail_bytes(n) + (size_t)wid * walk_private_bytes(n), n);
   walk_init_private(wm, n, lane);
-  if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n + 1);
+  if (threadIdx.x == 0) tail[n] = (uint16_t)(2 * n);
 
   WalkQuota quota = {0, 0};
   int staged = -1;
@@ -578,7 +643,7 @@ dist_walk_shared_kernel(const int32_t *__restrict__ genomes, const int32_t *__re
         const int32_t *sp = sinv + (long long)pj * n;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
           const int s = sp[i];
-          tail[i] = (uint16_t)(s > 0 ? 2 * s - 1 : -2 * s);
+          tail[i] = walk_tail_entry(s);
         }
         staged = pj;
       }
