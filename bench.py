@@ -199,7 +199,7 @@ def run_reference_arm(args):
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit,clocks.mem")
 
     def __init__(self, index: int):
         self.index = index
@@ -224,7 +224,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, pw, extra = [], [], set(), [], {}
         for ts, ln in self.lines:
             if t0 is not None and not (t0 <= ts <= t1 + 0.2):
                 continue
@@ -239,10 +239,19 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
+            try:                                       # what tells two boxes of the pool apart
+                pw.append(float(f[3]))
+                extra = {"power_limit_w": float(f[9]), "mem_mhz": float(f[10])}
+            except (ValueError, IndexError):
+                pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if pw:
+            out["power_w"] = float(np.median(pw))
+        out.update(extra)
+        return out
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------

@@ -12,21 +12,26 @@
 //            neighbouring genes' ends are in its own registers.  An alternating cycle of the graph is
 //            two tau-orbits (one per direction); the orbit of its leftmost vertex q (always even) has
 //            label q, the other one label q+1.
-//   walks    every vertex that is a multiple of the node stride (2^shift) is a NODE; lane l may start
-//            walks at nodes l, l+32, ...  A walk CLAIMS its start (bit 15 of the H entry), then
-//            follows tau, claiming every vertex it reaches, until it arrives at a claimed vertex --
-//            which is always the start of a walk (tau is a bijection: a segment can only be entered
-//            through its first vertex).  It leaves one word: smallest vertex of the segment, id of
-//            the walk it ran into, "an oriented grey edge was crossed".  A lane whose walk ended takes
-//            the next unclaimed node of its list, which splits whatever long stretch that node lies
-//            on: the load balances itself.  Starts happen in a separate section of the loop, so a
-//            claim is never raced.  This replaces the sequential walk of classify_cycle_path
-//            (G/graph_edit.c:207-457) with ~1.4 * 2n/32 steps per lane and ~100 walks per pair.
+//   walks    one vertex in every 2^shift is a NODE (WalkGrid: a grid skewed so that 32 consecutive nodes
+//            lie in 32 banks); free nodes are handed to the lanes that are out of work.  A walk CLAIMS
+//            its start (bit 15 of the H entry), then follows tau, claiming every vertex it reaches,
+//            until it arrives at a claimed vertex -- which is always the start of a walk (tau is a
+//            bijection: a segment can only be entered through its first vertex).  It leaves one word:
+//            smallest vertex of the segment, id of the walk it ran into, "an oriented grey edge was
+//            crossed".  A lane whose walk ended takes the next free node, which splits whatever long
+//            stretch that node lies on: the load balances itself.  Starts happen in a separate
+//            section of the loop, so a claim is never raced.  This replaces the sequential walk of
+//            classify_cycle_path (G/graph_edit.c:207-457) with ~1.5 * 2n/32 steps per lane and ~85
+//            walks per pair.  A step carries the shared-memory ADDRESS of the entry under examination
+//            (7 instructions; the dependent chain is load -> test || add -> load).  Measured and
+//            rejected: claims on even vertices only -- fewer store wavefronts,
+//            but the second predicate costs more than they save.
 //   jumping  pointer jumping over the walk words only (registers, like dist_core's phase B); the
 //            walk whose own segment holds the orbit minimum is the orbit's root.
-//   rest     vertices never claimed lie on orbits without a node (short cycles): the lane that finds one
-//            in its part of H walks its orbit until it meets a smaller vertex; the one that gets round is
-//            the root.
+//   rest     EVEN vertices never claimed lie on orbits without a node (short cycles): the lane that finds
+//            one in its part of H walks its orbit until it meets a smaller vertex; the one that gets
+//            round is the root.  (Odd ones are not tried: an orbit with an odd minimum is the twin of the
+//            orbit that carries the cycle's label, and counts nothing.)
 //   result   c = number of roots with an even label; when no root is unoriented every component is
 //            oriented and d = b - c (the early exit of G/graph_components.c:522-527).  Unoriented
 //            cycles first get the cheap "covered by an oriented cycle" test of dist_core; a pair it
@@ -43,6 +48,15 @@
 #define GRSR_EMU_READ_BEFORE_WRITE_WARP() __syncwarp()
 #else
 #define GRSR_EMU_READ_BEFORE_WRITE_WARP() ((void)0)
+#endif
+
+// Emulator-only diagnostics (scripts/walk_occupancy.py): how many lanes take each tau step, how many
+// start sections a pair needs.  Never defined in a library build.
+#ifdef GRSR_WALK_STATS
+extern "C" unsigned long long g_walk_stats[64];
+#define GRSR_WALK_STAT(i, v) (g_walk_stats[i] += (v))
+#else
+#define GRSR_WALK_STAT(i, v) ((void)0)
 #endif
 
 namespace grsr {
@@ -393,6 +407,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
         }
       }
       W += served;
+      if (lane == 0) GRSR_WALK_STAT(44, 1);
       __syncwarp();
       if (!__any_sync(kFull, !ended)) break;
       const bool pool = (pc < K) && (W < kWalkMaxWalks);  // lanes out of work can still be served
@@ -400,12 +415,21 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       for (;;) {
 #pragma unroll
         for (int s = 0; s < kWalkGroup; s++) {
-          if (!(e & kVis)) {                            // unclaimed: claim it (even vertices only) and examine tau of it
-            if (at & 2u) walk_sts16(at, e | kVis);
+#ifdef GRSR_WALK_STATS
+          { const int act = __popc(__ballot_sync(kFull, !(e & kVis))); if (lane == 0) { GRSR_WALK_STAT(act, 1); GRSR_WALK_STAT(40 + (pool ? 0 : 1), 1); GRSR_WALK_STAT(42 + (pool ? 0 : 1), act); } }
+#endif
+          // unclaimed: claim it and examine tau of it.  The next address does not wait for the test, and
+          // the load the next step depends on is issued before the claim.  (One level of predication:
+          // a nested test makes the compiler branch, and a branch per step costs 8 %.)
+          const walk_addr_t nx = h1 + 2u * e;
+          if (!(e & kVis)) {
+            const unsigned claimed = e | kVis;
+            const walk_addr_t cur = at;
             mn = at < mn ? at : mn;
-            at = h1 + 2u * e;
-            orr |= at ^ org;
+            at = nx;
             e = walk_lds16(at);
+            walk_sts16(cur, claimed);
+            orr |= at ^ org;
           }
         }
         ended = (e & kVis) != 0u;
@@ -414,7 +438,7 @@ __device__ inline bool walk_pair(const WalkMem &wm, const int32_t *__restrict__ 
       }
       __syncwarp();                                   // nobody examines nodes while others still claim
     }
-    if (lane == 0) UL[0] = 0;                         // the scratch becomes the unoriented-cycle list
+    if (lane == 0) { UL[0] = 0; GRSR_WALK_STAT(45, 1); GRSR_WALK_STAT(46, W); }   // the scratch becomes the unoriented-cycle list
   }
   __syncwarp();
 

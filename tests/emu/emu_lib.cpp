@@ -3,6 +3,9 @@
 // exists.  Built by tests/emu/Makefile into tests/emu/libgrsr_emu.so; loaded only by tests/.
 #define GRSR_EMU 1
 #include "cuda_emu.hpp"
+#ifdef GRSR_WALK_STATS
+extern "C" { unsigned long long g_walk_stats[64]; }
+#endif
 #include "../../grsr_b200/csrc/grsr_core.cuh"
 #include "../../grsr_b200/csrc/grsr_scenario.cuh"
 #include "../../grsr_b200/csrc/grsr_stepwise.cuh"
