@@ -203,6 +203,10 @@ extern "C" int emu_dist_pairs_walk(const int32_t *genomes, int G, int n, const i
   return shared < 0 ? (int)((unsigned long long)flag * 64ull <= (unsigned long long)npairs) : 0;
 }
 
+// The walk kernel's node grid (grsr_walk.cuh WalkGrid), for the bank / mapping properties test.
+extern "C" int emu_walk_grid_vertex(int shift, int k) { return (int)grsr::WalkGrid(shift).vertex((unsigned)k); }
+extern "C" int emu_walk_grid_is_node(int shift, int x) { return grsr::WalkGrid(shift).is_node((unsigned)x) ? 1 : 0; }
+
 // grsr_unsigned_dist as the library computes it (host preprocessing of grsr_unsigned_host.hpp + the
 // sign-enumeration kernel), with the kernel run through the emulator.  info7 = {dist, approx, passes,
 // num_sing[0..1], num_doub[0..1]}.

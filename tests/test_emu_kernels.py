@@ -205,3 +205,22 @@ def test_emu_block_shapes_with_1024_threads(n, count, seed):
     g = U.mixed_genomes(n, count, seed=seed)
     pairs = np.array([[i, j] for i in range(count) for j in range(count)], dtype=np.int32)
     assert np.array_equal(U.emu_stats(g, pairs, threads=0, grid=2), U.orc_stats(g, pairs))
+
+
+@pytest.mark.parametrize("shift", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_walk_node_grid(shift):
+    """WalkGrid: node k sits in slot k (vertex >> shift == k) on an even vertex, is_node() recognises exactly
+    those vertices, and the H entries (16-bit index vertex + 1) of ANY 32 consecutive nodes lie in 32
+    different 4-byte banks -- the warp examines 32 nodes per shared-memory load."""
+    emu = U.emulator()
+    K = 300
+    v = [emu.emu_walk_grid_vertex(shift, k) for k in range(K)]
+    for k, x in enumerate(v):
+        assert x % 2 == 0 and x >> shift == k
+        assert emu.emu_walk_grid_is_node(shift, x) == 1
+    nodes = set(v)
+    for x in range(0, min(v[-1], 4000), 2):
+        assert emu.emu_walk_grid_is_node(shift, x) == (1 if x in nodes else 0)
+    for k0 in range(K - 32):
+        banks = {((x + 1) >> 1) % 32 for x in v[k0:k0 + 32]}
+        assert len(banks) == 32, (shift, k0)
